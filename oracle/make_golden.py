@@ -1,0 +1,86 @@
+"""TEST INFRASTRUCTURE -- generates tests/golden/*.npz by running the UNMODIFIED reference (both engines) through
+oracle/refload.py.  Run in the build container only (needs /root/reference):  python -m oracle.make_golden
+
+The fixtures pin (a) the NumPy oracle (tests/test_oracle_terrain.py, CPU) and (b) the CUDA path (tests -m gpu).
+"""
+
+from __future__ import annotations
+
+import os
+import warnings
+
+import numpy as np
+
+from oracle import synth
+from oracle.refload import load_reference
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+SURF = ["slope", "aspect", "hillshade", "curvature", "profile_curvature", "tangential_curvature",
+        "planform_curvature", "flowline_curvature", "max_curvature", "min_curvature"]
+WIN = ["topographic_position_index", "terrain_ruggedness_index", "roughness", "rugosity"]
+
+
+def terrain_inputs() -> dict[str, np.ndarray]:
+    frac = synth.inject_nans(synth.fractal_dem((40, 52)), frac=0.004, hole=3)
+    rng = np.random.default_rng(42)
+    noise = rng.normal(size=(11, 11)).astype(np.float32)  # like test_surfit.py:413-452 (normal DEM with one NaN)
+    noise[4, 6] = np.nan
+    integer = synth.integer_dem((24, 30))
+    integer[7, 9] = np.nan
+    small_int = synth.integer_dem((20, 22), seed=9, high=900)  # sums of squared diffs stay < 2^24: order-free
+    return {"fractal": frac, "noise": noise, "integer": integer, "small_int": small_int}
+
+
+def main() -> None:
+    warnings.filterwarnings("ignore")
+    ref = load_reference()
+    os.makedirs(OUT, exist_ok=True)
+    gta = ref.terrain.get_terrain_attribute
+    inputs = terrain_inputs()
+    store: dict[str, np.ndarray] = {f"in|{k}": v for k, v in inputs.items()}
+    res = 5.0
+    for name, dem in inputs.items():
+        for engine in ("scipy", "numba"):
+            for fit in ("Horn", "ZevenbergThorne", "Florinsky"):
+                for cm in ("geometric", "directional"):
+                    attrs = SURF[:3] if fit == "Horn" else SURF
+                    if fit == "Horn" and cm == "directional":
+                        continue
+                    for deg in (True, False):
+                        if not deg and not (name == "fractal" and cm == "geometric"):
+                            continue
+                        outs = gta(dem, attrs, resolution=res, surface_fit=fit, curv_method=cm, engine=engine,
+                                   degrees=deg)
+                        for a, o in zip(attrs, outs):
+                            if not deg and a not in ("slope", "aspect"):
+                                continue
+                            store[f"surf|{name}|{engine}|{fit}|{cm}|{'deg' if deg else 'rad'}|{a}"] = o
+            # hillshade variants
+            if name == "fractal":
+                for az, alt, zf in ((45.0, 10.0, 1.0), (315.0, 45.0, 3.0), (200.0, 80.0, 0.5)):
+                    for fit in ("Horn", "Florinsky"):
+                        o = gta(dem, "hillshade", resolution=res, surface_fit=fit, engine=engine,
+                                hillshade_azimuth=az, hillshade_altitude=alt, hillshade_z_factor=zf)
+                        store[f"hs|{name}|{engine}|{fit}|{az}|{alt}|{zf}"] = o
+            for w in (3, 5):
+                for tm in ("Riley", "Wilson"):
+                    attrs = WIN if w == 3 else WIN[:3]
+                    outs = gta(dem, attrs, resolution=res, window_size=w, tri_method=tm, engine=engine)
+                    for a, o in zip(attrs, outs):
+                        store[f"win|{name}|{engine}|{w}|{tm}|{a}"] = o
+    # float64 input (out_dtype follows the input dtype, terrain.py:328-332)
+    dem64 = inputs["fractal"].astype(np.float64) + 0.123456789
+    store["in|fractal64"] = dem64
+    for fit in ("ZevenbergThorne", "Florinsky"):
+        outs = gta(dem64, SURF, resolution=res, surface_fit=fit, engine="numba")
+        for a, o in zip(SURF, outs):
+            store[f"surf|fractal64|numba|{fit}|geometric|deg|{a}"] = o
+    outs = gta(dem64, WIN, resolution=res, window_size=3, engine="scipy")
+    for a, o in zip(WIN, outs):
+        store[f"win|fractal64|scipy|3|Riley|{a}"] = o
+    np.savez_compressed(os.path.join(OUT, "terrain_reference.npz"), **store)
+    print(f"terrain_reference.npz: {len(store)} arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,108 @@
+"""CPU: host-side logic (validation order, messages, dtype rules) and the C ABI surface -- no compute calls."""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+import warnings
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib_path() -> str:
+    from xdem_b200 import _lib
+
+    if not os.path.exists(_lib.LIB_PATH):
+        from xdem_b200 import build
+
+        build.build()
+    return _lib.LIB_PATH
+
+
+def test_abi_exports_every_declared_symbol() -> None:
+    header = open(os.path.join(ROOT, "include", "xdem_b200.h")).read()
+    declared = set(re.findall(r"\b(xb_[a-z0-9_]+)\s*\(", header))
+    L = ctypes.CDLL(_lib_path())
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, f"symbols declared in include/xdem_b200.h but not exported: {missing}"
+    L.xb_version.restype = ctypes.c_int
+    assert L.xb_version() >= 100
+    from xdem_b200 import _lib
+
+    assert set(_lib.EXPORTED) == declared
+
+
+def test_validation_messages_match_reference() -> None:
+    """terrain.py:296-400 / test_terrain.py:428-490 -- raised before any CUDA call."""
+    import xdem_b200.terrain as t
+
+    dem = np.ones((5, 5), dtype=np.float32)
+    with pytest.raises(ValueError, match="'Horn' surface fit method cannot be used for to calculate curvatures"):
+        t.get_terrain_attribute(dem, "profile_curvature", resolution=1.0, surface_fit="Horn")
+    with pytest.raises(ValueError, match="'resolution' must be provided as an argument for attributes"):
+        t.get_terrain_attribute(dem, "slope")
+    with pytest.raises(ValueError, match="Surface fit and rugosity require the same X and Y resolution"):
+        t.get_terrain_attribute(dem, "slope", resolution=(1.0, 2.0))
+    with pytest.raises(ValueError, match="Attribute 'foo' is not supported"):
+        t.get_terrain_attribute(dem, "foo", resolution=1.0)
+    with pytest.raises(ValueError, match="Surface fit 'bar' is not supported"):
+        t.get_terrain_attribute(dem, "slope", resolution=1.0, surface_fit="bar")
+    with pytest.raises(ValueError, match="Curvature method 'x' is not supported"):
+        t.get_terrain_attribute(dem, "slope", resolution=1.0, curv_method="x")
+    with pytest.raises(ValueError, match="TRI method 'x' is not supported"):
+        t.get_terrain_attribute(dem, "terrain_ruggedness_index", tri_method="x")
+    with pytest.raises(ValueError, match="Azimuth must be a value between 0 and 360"):
+        t.hillshade(dem, azimuth=361.0, resolution=1.0)
+    with pytest.raises(ValueError, match="Altitude must be a value between 0 and 90"):
+        t.hillshade(dem, altitude=91.0, resolution=1.0)
+    with pytest.raises(ValueError, match="z_factor must be a non-negative finite value"):
+        t.hillshade(dem, z_factor=np.inf, resolution=1.0)
+    with pytest.warns(DeprecationWarning, match="'slope_method' is deprecated"):
+        with pytest.raises(ValueError, match="cannot be used for to calculate curvatures"):
+            t.get_terrain_attribute(dem, "max_curvature", resolution=1.0, slope_method="Horn")
+    with pytest.warns(DeprecationWarning, match="'method' is deprecated"):
+        with pytest.raises(ValueError):
+            t.slope(dem, method="nope", resolution=1.0)
+    with pytest.warns(DeprecationWarning, match="The curvature attribute is deprecated"):
+        with pytest.raises(ValueError):
+            t.curvature(dem, resolution=1.0, surface_fit="nope")
+
+
+def test_out_of_scope_attributes_fail_loudly() -> None:
+    import xdem_b200.terrain as t
+
+    dem = np.ones((20, 20), dtype=np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with pytest.raises(NotImplementedError):
+            t.fractal_roughness(dem)
+        with pytest.raises(NotImplementedError):
+            t.texture_shading(dem)
+        with pytest.raises(NotImplementedError):
+            t.roughness(dem, window_size=7)
+
+
+def test_no_cpu_fallback() -> None:
+    """Without a CUDA device every compute entry point must raise (never silently compute on the CPU)."""
+    import torch
+
+    import xdem_b200.terrain as t
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        t.slope(np.ones((8, 8), dtype=np.float32), resolution=1.0)
+
+
+def test_product_never_imports_oracle() -> None:
+    """The oracle is test infrastructure: nothing under xdem_b200/ may import it."""
+    pkg = os.path.join(ROOT, "xdem_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"

@@ -1,0 +1,304 @@
+"""GPU parity tests of the fused terrain kernel, through the public API -> ctypes C ABI -> CUDA.
+
+Compared against (a) fixtures produced by the unmodified reference (both engines), (b) the NumPy oracle on seeded
+inputs, (c) the reference's known-answer tests, (d) size-independent properties at large sizes."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+SURF = ["slope", "aspect", "hillshade", "curvature", "profile_curvature", "tangential_curvature",
+        "planform_curvature", "flowline_curvature", "max_curvature", "min_curvature"]
+WIN = ["topographic_position_index", "terrain_ruggedness_index", "roughness", "rugosity"]
+
+
+@pytest.fixture(scope="module")
+def G() -> dict[str, np.ndarray]:
+    return parity.load_golden()
+
+
+@pytest.fixture(scope="module")
+def xb():
+    import xdem_b200
+
+    return xdem_b200
+
+
+def _keep(dem: np.ndarray, fit: str) -> np.ndarray:
+    from oracle import terrain_oracle as to
+
+    s = to.get_terrain_attribute(dem.astype(np.float64), "slope", resolution=5.0, surface_fit=fit)
+    return s > 1e-3
+
+
+@pytest.mark.parametrize("name", ["fractal", "noise", "integer"])
+@pytest.mark.parametrize("fit", ["Horn", "ZevenbergThorne", "Florinsky"])
+@pytest.mark.parametrize("cm", ["geometric", "directional"])
+def test_surface_vs_reference_fixtures(xb, G, name: str, fit: str, cm: str) -> None:
+    if fit == "Horn" and cm == "directional":
+        pytest.skip("Horn has no curvatures")
+    dem = G[f"in|{name}"]
+    attrs = SURF[:3] if fit == "Horn" else SURF
+    outs = xb.terrain.get_terrain_attribute(dem, attrs, resolution=5.0, surface_fit=fit, curv_method=cm)
+    keep = _keep(dem, fit)
+    for a, o in zip(attrs, outs):
+        for engine in ("numba", "scipy"):
+            ref = G[f"surf|{name}|{engine}|{fit}|{cm}|deg|{a}"]
+            # the reference's SciPy engine rounds its coefficients to float32: its own two engines agree to ~1e-4 rel
+            # on near-zero values, so the SciPy fixtures get the wider absolute term
+            scale = (1.0 if engine == "numba" else 30.0) * (1.0 if name == "fractal" else 50.0)
+            parity.assert_attr_close(o, ref, a, where=keep, atol_scale=scale, msg=f"{name}/{engine}/{fit}/{cm}")
+
+
+def test_radians_and_seam(xb, G) -> None:
+    from xdem_b200.surfit import _get_surface_attributes
+
+    dem = G["in|fractal"]
+    for fit in ("Horn", "ZevenbergThorne", "Florinsky"):
+        out = xb.terrain.get_terrain_attribute(dem, ["slope", "aspect"], resolution=5.0, surface_fit=fit,
+                                               degrees=False)
+        seam = _get_surface_attributes(dem, 5.0, ["aspect", "hillshade", "slope"], surface_fit=fit)
+        assert seam.shape == (3,) + dem.shape and seam.dtype == np.float32
+        for a, o in zip(["slope", "aspect"], out):
+            ref = G[f"surf|fractal|numba|{fit}|geometric|rad|{a}"]
+            parity.assert_attr_close(o, ref, a, degrees=False, where=_keep(dem, fit), msg=f"rad {fit}")
+        assert np.array_equal(seam[2], out[0], equal_nan=True)
+        assert np.array_equal(seam[0], out[1], equal_nan=True)
+
+
+def test_hillshade_variants(xb, G) -> None:
+    dem = G["in|fractal"]
+    for az, alt, zf in ((45.0, 10.0, 1.0), (315.0, 45.0, 3.0), (200.0, 80.0, 0.5)):
+        for fit in ("Horn", "Florinsky"):
+            o = xb.terrain.hillshade(dem, surface_fit=fit, azimuth=az, altitude=alt, z_factor=zf, resolution=5.0)
+            ref = G[f"hs|fractal|numba|{fit}|{az}|{alt}|{zf}"]
+            parity.assert_attr_close(o, ref, "hillshade", msg=f"hs {fit} {az} {alt} {zf}")
+            assert np.nanmin(o) >= 0 and np.nanmax(o) <= 255
+
+
+@pytest.mark.parametrize("name", ["fractal", "integer", "small_int"])
+@pytest.mark.parametrize("w", [3, 5])
+@pytest.mark.parametrize("tm", ["Riley", "Wilson"])
+def test_windowed_vs_reference_fixtures(xb, G, name: str, w: int, tm: str) -> None:
+    dem = G[f"in|{name}"]
+    attrs = WIN if w == 3 else WIN[:3]
+    outs = xb.terrain.get_terrain_attribute(dem, attrs, resolution=5.0, window_size=w, tri_method=tm)
+    for a, o in zip(attrs, outs):
+        ref_n = G[f"win|{name}|numba|{w}|{tm}|{a}"]
+        ref_s = G[f"win|{name}|scipy|{w}|{tm}|{a}"]
+        assert o.dtype == np.float32
+        assert parity.nanmask_equal(o, ref_n) and parity.nanmask_equal(o, ref_s), a
+        if a == "roughness":
+            assert np.array_equal(o, ref_s, equal_nan=True) and np.array_equal(o, ref_n, equal_nan=True)
+        elif a == "rugosity":
+            assert np.array_equal(o, ref_s, equal_nan=True), "rugosity must be bit-exact vs the SciPy engine"
+        elif a == "topographic_position_index":
+            if name != "fractal":
+                assert np.array_equal(o, ref_s, equal_nan=True), "TPI must be bit-exact on integer-valued DEMs"
+            if w == 3:
+                assert np.array_equal(o, ref_n, equal_nan=True)
+            assert np.nanmax(np.abs(o - ref_s)) <= 4 * np.spacing(np.float32(np.nanmax(np.abs(dem)) * w * w))
+        else:
+            assert np.array_equal(o, ref_n, equal_nan=True), "TRI must be bit-exact vs the Numba engine"
+            if name == "small_int" or tm == "Wilson":
+                assert np.array_equal(o, ref_s, equal_nan=True)
+
+
+def test_float64_input(xb, G) -> None:
+    dem = G["in|fractal64"]
+    for fit in ("ZevenbergThorne", "Florinsky"):
+        outs = xb.terrain.get_terrain_attribute(dem, SURF, resolution=5.0, surface_fit=fit)
+        for a, o in zip(SURF, outs):
+            ref = G[f"surf|fractal64|numba|{fit}|geometric|deg|{a}"]
+            assert o.dtype == np.float64
+            parity.assert_attr_close(o, ref, a, rtol=1e-9, atol_scale=1e-4, msg=f"f64 {fit}")
+    outs = xb.terrain.get_terrain_attribute(dem, WIN, resolution=5.0)
+    for a, o in zip(WIN, outs):
+        ref = G[f"win|fractal64|scipy|3|Riley|{a}"]
+        assert o.dtype == np.float64
+        parity.assert_attr_close(o, ref, a, rtol=1e-12, atol_scale=1e-6, msg="f64 windowed")
+
+
+def test_fused_equals_separate_and_order(xb, G) -> None:
+    """multi-attribute == single-attribute (test_terrain.py:248-293), any request order, surface+windowed fused."""
+    dem = G["in|fractal"]
+    req = ["roughness", "slope", "rugosity", "max_curvature", "aspect", "topographic_position_index", "hillshade"]
+    outs = xb.terrain.get_terrain_attribute(dem, req, resolution=5.0)
+    for a, o in zip(req, outs):
+        single = xb.terrain.get_terrain_attribute(dem, a, resolution=5.0)
+        assert np.array_equal(o, single, equal_nan=True), a
+    # mixed halos: 3x3 fit with 5x5 window and 5x5 fit with 3x3 window
+    a1 = xb.terrain.get_terrain_attribute(dem, ["slope", "roughness"], resolution=5.0, surface_fit="Horn",
+                                          window_size=5)
+    assert np.array_equal(a1[0], xb.terrain.slope(dem, surface_fit="Horn", resolution=5.0), equal_nan=True)
+    assert np.array_equal(a1[1], xb.terrain.roughness(dem, window_size=5), equal_nan=True)
+
+
+def test_reference_doctests(xb) -> None:
+    """terrain.py:268-279, 799-813, 1484-1493, 1553-1562."""
+    dem = np.repeat(np.arange(3), 3)[::-1].reshape(3, 3)
+    s, a = xb.terrain.get_terrain_attribute(dem, ["slope", "aspect"], resolution=1, surface_fit="ZevenbergThorne")
+    assert s[1, 1] == np.float32(45.0) and a[1, 1] == np.float32(180.0)
+    assert xb.terrain.aspect(np.tile(np.arange(3), (3, 1)), surface_fit="ZevenbergThorne")[1, 1] == np.float32(270.0)
+    d3 = np.zeros((3, 3), dtype="int32")
+    d3[1, 1] = 1
+    assert xb.terrain.topographic_position_index(d3)[1, 1] == np.float32(1.0)
+    assert xb.terrain.terrain_ruggedness_index(d3)[1, 1] == np.float32(2.828427)
+    assert xb.terrain.roughness(d3)[1, 1] == np.float32(1.0)
+
+
+def test_rugosity_known_answers(xb) -> None:
+    """test_window.py:21-68."""
+    dem = np.array([[190, 170, 155], [183, 165, 145], [175, 160, 122]], dtype="float32")
+    assert xb.terrain.rugosity(dem, resolution=100.0)[1, 1] == pytest.approx(10280.48 / 10000.0, rel=1e-4)
+    for dh in np.linspace(0.01, 100, 3):
+        for resolution in np.linspace(0.01, 100, 3):
+            d = np.array([[1, 1, 1], [1, 1 + dh, 1], [1, 1, 1]], dtype="float64")
+            r = xb.terrain.rugosity(d, resolution=resolution)
+            side1 = np.sqrt(2 * resolution**2 + dh**2) / 2.0
+            side2 = np.sqrt(resolution**2 + dh**2) / 2.0
+            side3 = resolution / 2.0
+            s = (side1 + side2 + side3) / 2.0
+            A = np.sqrt(s * (s - side1) * (s - side2) * (s - side3))
+            assert r[1, 1] == pytest.approx(8 * A / resolution**2, rel=1e-6)
+
+
+@pytest.mark.parametrize("fit,w", [("Horn", 3), ("ZevenbergThorne", 3), ("Florinsky", 5)])
+def test_nan_propagation_surface(xb, fit: str, w: int) -> None:
+    """test_surfit.py:467-518: NaN mask == binary_dilation(nanmask, ones(w,w)) + hw-wide border, exactly."""
+    from scipy.ndimage import binary_dilation
+
+    rng = np.random.default_rng(42)
+    dem = rng.normal(size=(37, 53)).astype(np.float32)
+    dem[rng.integers(0, 37, 9), rng.integers(0, 53, 9)] = np.nan
+    dem[20, 30] = np.inf
+    attrs = SURF[:3] if fit == "Horn" else SURF
+    outs = xb.terrain.get_terrain_attribute(dem, attrs, resolution=1.0, surface_fit=fit)
+    expected = binary_dilation(~np.isfinite(dem), structure=np.ones((w, w), bool))
+    hw = w // 2
+    expected[:hw] = expected[-hw:] = True
+    expected[:, :hw] = expected[:, -hw:] = True
+    for a, o in zip(attrs, outs):
+        assert np.array_equal(np.isnan(o), expected), (fit, a)
+
+
+@pytest.mark.parametrize("w", [3, 5])
+def test_nan_propagation_windowed(xb, w: int) -> None:
+    """test_window.py:194-239."""
+    from scipy.ndimage import binary_dilation
+
+    rng = np.random.default_rng(7)
+    dem = rng.normal(size=(29, 41)).astype(np.float32)
+    dem[rng.integers(0, 29, 6), rng.integers(0, 41, 6)] = np.nan
+    attrs = WIN if w == 3 else WIN[:3]
+    outs = xb.terrain.get_terrain_attribute(dem, attrs, resolution=1.0, window_size=w)
+    expected = binary_dilation(~np.isfinite(dem), structure=np.ones((w, w), bool))
+    hw = w // 2
+    expected[:hw] = expected[-hw:] = True
+    expected[:, :hw] = expected[:, -hw:] = True
+    for a, o in zip(attrs, outs):
+        assert np.array_equal(np.isnan(o), expected), a
+
+
+def test_synthetic_curvature_signs(xb) -> None:
+    """test_surfit.py:228-411 (planes -> 0, ridge/trough antisymmetry)."""
+    yy, xx = np.mgrid[0:21, 0:21].astype(np.float32)
+    plane = (2.0 * xx + 3.0 * yy + 100).astype(np.float32)
+    curv = [a for a in SURF if "curvature" in a]
+    for fit in ("ZevenbergThorne", "Florinsky"):
+        outs = xb.terrain.get_terrain_attribute(plane, curv, resolution=1.0, surface_fit=fit)
+        for a, o in zip(curv, outs):
+            assert np.nanmax(np.abs(o)) < 1e-4, (fit, a)
+        ridge = (-np.abs(xx - 10) * 2 + 50).astype(np.float32)
+        r = xb.terrain.get_terrain_attribute(ridge, curv, resolution=1.0, surface_fit=fit)
+        t = xb.terrain.get_terrain_attribute(-ridge, curv, resolution=1.0, surface_fit=fit)
+        for a, ro, to_ in zip(curv, r, t):
+            if a in ("max_curvature", "min_curvature"):
+                continue
+            assert np.allclose(ro, -to_, equal_nan=True, atol=1e-5), (fit, a)
+        rmax = xb.terrain.max_curvature(ridge, resolution=1.0, surface_fit=fit)
+        tmin = xb.terrain.min_curvature(-ridge, resolution=1.0, surface_fit=fit)
+        assert np.allclose(rmax, -tmin, equal_nan=True, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (2, 7), (5, 130), (257, 131), (64, 128), (300, 1027)])
+def test_odd_shapes_vs_oracle(xb, shape) -> None:
+    """Ragged / tiny / unaligned rasters (non-TMA loader, scalar store tails) against the oracle."""
+    from oracle import synth
+    from oracle import terrain_oracle as to
+
+    dem = synth.fractal_dem(shape, seed=3)
+    if dem.size > 50:
+        dem = synth.inject_nans(dem, frac=0.002, hole=2)
+    req = ["slope", "aspect", "hillshade", "curvature", "topographic_position_index", "roughness"]
+    for fit in ("ZevenbergThorne", "Florinsky"):
+        outs = xb.terrain.get_terrain_attribute(dem, req, resolution=5.0, surface_fit=fit, window_size=5)
+        refs = to.get_terrain_attribute(dem, req, resolution=5.0, surface_fit=fit, window_size=5)
+        keep = to.get_terrain_attribute(dem.astype(np.float64), "slope", resolution=5.0, surface_fit=fit) > 1e-3
+        for a, o, r in zip(req, outs, refs):
+            if a == "topographic_position_index":
+                assert parity.nanmask_equal(o, r)
+                assert np.array_equal(o, r, equal_nan=True)
+            else:
+                parity.assert_attr_close(o, r, a, where=keep, msg=f"{shape} {fit}")
+
+
+def test_torch_cuda_tensor_in_out(xb) -> None:
+    import torch
+
+    from oracle import synth
+
+    dem = synth.fractal_dem((200, 260), seed=5)
+    t = torch.from_numpy(dem).cuda()
+    s_t = xb.terrain.slope(t, resolution=5.0)
+    assert isinstance(s_t, torch.Tensor) and s_t.is_cuda and s_t.dtype == torch.float32
+    s_n = xb.terrain.slope(dem, resolution=5.0)
+    assert np.array_equal(s_t.cpu().numpy(), s_n, equal_nan=True)
+    # non-contiguous view / unaligned base -> cooperative loader path gives identical results
+    big = torch.full((204, 271), float("nan"), device="cuda")
+    big[2:202, 5:265] = t
+    s_v = xb.terrain.slope(big[2:202, 5:265], resolution=5.0)
+    assert np.array_equal(s_v.cpu().numpy(), s_n, equal_nan=True)
+
+
+def test_large_tiled_equals_untiled(xb) -> None:
+    """Size-independent property at a large size (test_terrain.py:295-341 analogue): computing row blocks with halo rows
+    reproduces the single-launch result bit-for-bit; integer DEM windowed indexes stay bit-exact vs the oracle on a crop."""
+    import torch
+
+    from oracle import terrain_oracle as to
+    from xdem_b200 import _engine
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    H, W = 4096, 4096
+    z = (1000 + 0.05 * torch.cumsum(torch.cumsum(torch.randn((H, W), generator=g, device="cuda"), 0), 1)).float()
+    z[1000:1010, 2000:2020] = float("nan")
+    surf = ["slope", "aspect", "hillshade", "curvature", "max_curvature"]
+    win = ["topographic_position_index", "terrain_ruggedness_index", "roughness"]
+    full = _engine.terrain_fused(z, 5.0, surf, win, surface_fit="Florinsky", window_size=5, degrees=True,
+                                 clip_hillshade=True)
+    depth = 2
+    pieces = []
+    for r0 in range(0, H, 1000):
+        r1 = min(H, r0 + 1000)
+        b0, b1 = max(0, r0 - depth), min(H, r1 + depth)
+        pieces.append(_engine.terrain_fused(z[b0:b1], 5.0, surf, win, surface_fit="Florinsky", window_size=5,
+                                            degrees=True, clip_hillshade=True, row_begin=r0 - b0, row_end=r1 - b0))
+    tiled = torch.cat(pieces, dim=1)
+    # interior block edges must match exactly; the buffer ends act as raster borders only at the true borders
+    assert torch.equal(torch.isnan(full), torch.isnan(tiled))
+    assert torch.equal(torch.nan_to_num(full), torch.nan_to_num(tiled))
+    crop = z[990:1100, 1990:2120].cpu().numpy()
+    o = full[:, 990:1100, 1990:2120].cpu().numpy()[:, 2:-2, 2:-2]
+    r = to.get_terrain_attribute(crop, surf + win, resolution=5.0, surface_fit="Florinsky", window_size=5)
+    for i, a in enumerate(surf + win):
+        rr = r[i][2:-2, 2:-2]
+        if a == "topographic_position_index":
+            assert np.nanmax(np.abs(o[i] - rr)) < 1e-3
+        else:
+            parity.assert_attr_close(o[i], rr, a, msg="crop")

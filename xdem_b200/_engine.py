@@ -1,0 +1,89 @@
+"""Thin typed layer over the C ABI: allocates output planes as torch.cuda tensors and launches the CUDA kernels."""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Sequence
+
+import torch
+
+from . import _lib
+
+SURFACE_ORDER = ["slope", "aspect", "hillshade", "curvature", "profile_curvature", "tangential_curvature",
+                 "planform_curvature", "flowline_curvature", "max_curvature", "min_curvature"]  # surfit.py:407-418
+WINDOW_ORDER = ["topographic_position_index", "terrain_ruggedness_index", "roughness", "rugosity"]  # window.py:752-758
+FIT_IDS = {"horn": 0, "zevenbergthorne": 1, "florinsky": 2}  # surfit.py:1240
+CURV_IDS = {"geometric": 0, "directional": 1}  # surfit.py:1244
+N_PLANES = 14
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return 0
+    if t.dtype == torch.float64:
+        return 1
+    raise TypeError(f"unsupported raster dtype {t.dtype}")
+
+
+def terrain_fused(
+    dem: torch.Tensor,
+    resolution: float,
+    surface_attributes: Sequence[str] = (),
+    windowed_indexes: Sequence[str] = (),
+    surface_fit: str = "Florinsky",
+    curv_method: str = "geometric",
+    tri_method: str = "Riley",
+    window_size: int = 3,
+    degrees: bool = False,
+    clip_hillshade: bool = False,
+    hillshade_azimuth: float = 315.0,
+    hillshade_altitude: float = 45.0,
+    hillshade_z_factor: float = 1.0,
+    row_begin: int = 0,
+    row_end: int | None = None,
+    out: torch.Tensor | None = None,
+) -> torch.Tensor:
+    """One fused pass (xb_terrain_fused).  Returns a (n_attr, rows, cols) CUDA tensor whose planes follow
+    ``list(surface_attributes) + list(windowed_indexes)``.  ``dem`` may carry halo rows: only rows
+    [row_begin,row_end) are produced, rows outside the buffer count as NaN."""
+    if not dem.is_cuda or dem.dim() != 2:
+        raise ValueError("dem must be a 2-D CUDA tensor")
+    if dem.stride(1) != 1:
+        dem = dem.contiguous()
+    L = _lib.lib()
+    rows_buf, cols = dem.shape
+    ld = dem.stride(0)
+    if row_end is None:
+        row_end = rows_buf
+    names = list(surface_attributes) + list(windowed_indexes)
+    n_rows = row_end - row_begin
+    if out is None:
+        out = torch.empty((len(names), n_rows, cols), dtype=dem.dtype, device=dem.device)
+    elif out.shape != (len(names), n_rows, cols) or out.dtype != dem.dtype or not out.is_contiguous():
+        raise ValueError("bad `out` tensor")
+    planes = (ctypes.c_void_p * N_PLANES)()
+    surf_mask = 0
+    win_mask = 0
+    for i, a in enumerate(names):
+        if i < len(surface_attributes):
+            slot = SURFACE_ORDER.index(a)
+            if surf_mask >> slot & 1:
+                raise ValueError(f"duplicate attribute {a}")
+            surf_mask |= 1 << slot
+        else:
+            j = WINDOW_ORDER.index(a)
+            slot = 10 + j
+            if win_mask >> j & 1:
+                raise ValueError(f"duplicate attribute {a}")
+            win_mask |= 1 << j
+        planes[slot] = out[i].data_ptr()
+    stream = torch.cuda.current_stream(dem.device).cuda_stream
+    with torch.cuda.device(dem.device):
+        rc = L.xb_terrain_fused(
+            dem.data_ptr(), _dtype_code(dem), rows_buf, cols, ld, row_begin, row_end, float(resolution),
+            FIT_IDS[surface_fit.lower()], CURV_IDS[curv_method.lower()], surf_mask, win_mask, int(window_size),
+            0 if tri_method.lower() == "riley" else 1, int(bool(degrees)), int(bool(clip_hillshade)),
+            float(hillshade_azimuth), float(hillshade_altitude), float(hillshade_z_factor), planes, cols,
+            ctypes.c_void_p(stream))
+    _lib.check(rc)
+    return out

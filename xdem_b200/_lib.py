@@ -1,0 +1,60 @@
+"""ctypes binding of libxdem_b200.so (include/xdem_b200.h).  There is NO fallback: if the CUDA library is missing or a
+call fails, an exception is raised."""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxdem_b200.so")
+
+_lib: ctypes.CDLL | None = None
+
+
+class XdemB200Error(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Load the CUDA library (built by ``python -m xdem_b200.build`` / ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise XdemB200Error(
+            f"{LIB_PATH} not found: build the CUDA extension first (python -m xdem_b200.build). "
+            "xdem_b200 has no CPU fallback."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    L.xb_last_error.restype = c_char_p
+    L.xb_version.restype = c_int
+    L.xb_launch_count.restype = c_uint64
+    L.xb_terrain_fused.restype = c_int
+    L.xb_terrain_fused.argtypes = [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_double, c_int,
+                                   c_int, c_uint32, c_uint32, c_int, c_int, c_int, c_int, c_double, c_double,
+                                   c_double, ctypes.POINTER(c_void_p), c_int64, c_void_p]
+    if hasattr(L, "xb_terrain_fused_host"):
+        L.xb_terrain_fused_host.restype = c_int
+        L.xb_terrain_fused_host.argtypes = [c_void_p, c_int, c_int64, c_int64, c_double, c_int, c_int, c_uint32,
+                                            c_uint32, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
+                                            ctypes.POINTER(c_void_p), c_int64]
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().xb_last_error().decode("utf-8", "replace")
+        raise XdemB200Error(f"libxdem_b200 error {rc}: {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().xb_launch_count())
+
+
+#: every symbol declared in include/xdem_b200.h (checked by tests/test_abi.py)
+EXPORTED = ["xb_last_error", "xb_version", "xb_launch_count", "xb_terrain_fused"]
+
+__all__ = ["lib", "check", "launch_count", "XdemB200Error", "LIB_PATH", "EXPORTED", "c_int32"]

@@ -1,0 +1,36 @@
+// xdem_b200 -- parameters of the fused terrain kernel (K1)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define XB_FIT_HORN_ID 0
+#define XB_FIT_ZT_ID 1
+#define XB_FIT_FLORINSKY_ID 2
+
+namespace xbt {
+
+struct TerrainParams {
+    const void* dem;       // device raster buffer
+    long long rows_buf;    // rows of the buffer (rows outside are NaN)
+    long long cols;
+    long long ld;          // leading dimension (elements)
+    long long row_begin;   // output rows [row_begin,row_end)
+    long long row_end;
+    void* out[14];         // planes: 0..9 surface attributes, 10..13 windowed indexes (NULL if not requested)
+    long long out_ld;
+    long long tiles_x, ntiles;
+    uint32_t surf_mask, win_mask;
+    int fit_id;            // 0 Horn, 1 ZevenbergThorne, 2 Florinsky
+    int curv_dir;          // 0 geometric, 1 directional
+    int tri_wilson;        // 0 Riley, 1 Wilson
+    int degrees, clip_hs, vec_ok;
+    double inv_d1, inv_d2, inv_d3;  // 1/divider of (z_x,z_y), (z_xx,z_yy), z_xy  (surfit.py:278-304)
+    double rad2deg;
+    double hs_sin_alt, hs_kx, hs_ky, zf2;  // hillshade constants (surfit.py:606-622)
+    double rug_dl2_diag, rug_dl2_straight, rug_dl2_edge, rug_ll;  // rugosity constants in the DEM dtype
+};
+
+int launch(const TerrainParams& p, int dtype, int hs, int hw, cudaStream_t stream);
+int tile_rows(int halo);
+
+}  // namespace xbt
