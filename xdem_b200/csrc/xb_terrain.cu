@@ -510,9 +510,15 @@ terrain_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                                         a2 = heron(h[1], h[2], h[9]), a3 = heron(h[2], h[4], h[14]),
                                         a4 = heron(h[4], h[7], h[15]), a5 = heron(h[7], h[6], h[11]),
                                         a6 = heron(h[6], h[5], h[10]), a7 = heron(h[5], h[3], h[13]);
-                                // np.sum over 8 contiguous elements: pairwise tree ((a0+a1)+(a2+a3))+((a4+a5)+(a6+a7))
-                                const T area = Num<T>::add(Num<T>::add(Num<T>::add(a0, a1), Num<T>::add(a2, a3)),
-                                                           Num<T>::add(Num<T>::add(a4, a5), Num<T>::add(a6, a7)));
+                                // np.sum(A, axis=-1) on the (..., 8) block reduces with the short axis outermost,
+                                // i.e. sequentially (pinned by the SciPy-engine fixtures)
+                                T area = Num<T>::add(a0, a1);
+                                area = Num<T>::add(area, a2);
+                                area = Num<T>::add(area, a3);
+                                area = Num<T>::add(area, a4);
+                                area = Num<T>::add(area, a5);
+                                area = Num<T>::add(area, a6);
+                                area = Num<T>::add(area, a7);
                                 rug[k] = Num<T>::add(Num<T>::div(area, (T)p.rug_ll), carr);
                             }
                         }
