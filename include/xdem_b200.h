@@ -79,6 +79,16 @@ int xb_terrain_fused(const void* dem_dev, int dtype, int64_t rows_buf, int64_t c
                      double hillshade_azimuth, double hillshade_altitude, double hillshade_z_factor,
                      void* const* out_planes_host, int64_t out_ld, void* stream);
 
+/* Same computation from/to HOST buffers (pinned memory recommended): the raster is streamed through the GPU in row
+ * blocks with `depth` halo rows (the reference's tiling analogue: geoutils.map_overlap_multiproc_save,
+ * terrain.py:412-466), H2D / kernel / D2H overlapped on three streams.  This is the call the `e2e` benchmark figure
+ * times.  out_planes_host[i] are HOST pointers here; rows_per_block <= 0 picks ~96 MiB blocks. */
+int xb_terrain_fused_host(const void* dem_host, int dtype, int64_t rows, int64_t cols, double resolution, int fit_id,
+                          int curv_method_id, uint32_t surf_mask, uint32_t win_mask, int window_size,
+                          int tri_method_id, int degrees, int clip_hillshade, double hillshade_azimuth,
+                          double hillshade_altitude, double hillshade_z_factor, void* const* out_planes_host,
+                          int64_t rows_per_block);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,3 +136,26 @@ def test_oracle_vs_live_reference_random() -> None:
     o = to.get_terrain_attribute(dem, SURF, resolution=2.0, surface_fit="Florinsky")
     for a, oo, rr in zip(SURF, o, r):
         parity.assert_attr_close(oo, rr, a, msg="live")
+
+
+@pytest.mark.parametrize("name", ["fractal", "noise", "integer"])
+@pytest.mark.parametrize("fit", ["Horn", "ZevenbergThorne", "Florinsky"])
+def test_c_oracle_bit_exact_vs_numba_engine(name: str, fit: str) -> None:
+    """The plain-C restatement (oracle/terrain_oracle.c, the CPU-baseline arm) reproduces the reference's Numba engine
+    bit-for-bit on the committed fixtures."""
+    from oracle import c_oracle as co
+
+    dem = G[f"in|{name}"]
+    attrs = SURF[:3] if fit == "Horn" else SURF
+    for cm in ("geometric", "directional"):
+        if fit == "Horn" and cm == "directional":
+            continue
+        o = co.surface_attributes(dem, 5.0, attrs, fit, curv_method=cm, degrees=True, clip_hillshade=True)
+        for i, a in enumerate(attrs):
+            ref = G[f"surf|{name}|numba|{fit}|{cm}|deg|{a}"]
+            assert np.array_equal(o[i], ref, equal_nan=True), (name, fit, cm, a)
+    for w in (3, 5):
+        for tm in ("Riley", "Wilson"):
+            ww = co.windowed_indexes(dem, w, WIN[:3], tri_method=tm)
+            for i, a in enumerate(WIN[:3]):
+                assert np.array_equal(ww[i], G[f"win|{name}|numba|{w}|{tm}|{a}"], equal_nan=True), (name, w, tm, a)

@@ -302,3 +302,32 @@ def test_large_tiled_equals_untiled(xb) -> None:
             assert np.nanmax(np.abs(o[i] - rr)) < 1e-3
         else:
             parity.assert_attr_close(o[i], rr, a, msg="crop")
+
+
+def test_math_accuracy_sweep(xb) -> None:
+    """The branch-free fp32 atan / atan2 / sqrt / rsqrt cores (csrc/xb_math.cuh): sweep every gradient direction and
+    eleven decades of gradient magnitude on planar facets and compare with the float64 oracle at a few fp32 ulp."""
+    from oracle import terrain_oracle as to
+
+    n_ang, n_mag, B = 96, 48, 6
+    H, W = n_mag * B, n_ang * B
+    yy, xx = np.mgrid[0:H, 0:W]
+    ang = (xx // B) * (2 * np.pi / n_ang) + 0.0123
+    mag = 10.0 ** (-5 + 8 * (yy // B) / (n_mag - 1))
+    # planar facet per block, anchored at the block centre so that values stay fp32-friendly
+    cx, cy = (xx % B) - B / 2, (yy % B) - B / 2
+    dem = (100.0 + mag * (np.cos(ang) * cx + np.sin(ang) * cy)).astype(np.float32)
+    for fit in ("Horn", "ZevenbergThorne"):
+        out = xb.terrain.get_terrain_attribute(dem, ["slope", "aspect", "hillshade"], resolution=1.0, surface_fit=fit,
+                                               hillshade_z_factor=2.0)
+        ref = to.get_terrain_attribute(dem.astype(np.float64), ["slope", "aspect", "hillshade"], resolution=1.0,
+                                       surface_fit=fit, hillshade_z_factor=2.0)
+        for a, o, r in zip(["slope", "aspect", "hillshade"], out, ref):
+            m = np.isfinite(r) & (ref[0] > 1e-30)
+            d = np.abs(o[m].astype(np.float64) - r[m])
+            if a == "aspect":
+                d = np.minimum(d, 360.0 - d)
+                rel = d / 360.0
+            else:
+                rel = d / np.maximum(np.abs(r[m]), 1e-300)
+            assert rel.max() < 6e-7, (fit, a, rel.max())

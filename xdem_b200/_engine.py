@@ -5,6 +5,7 @@ from __future__ import annotations
 import ctypes
 from typing import Sequence
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -85,5 +86,71 @@ def terrain_fused(
             0 if tri_method.lower() == "riley" else 1, int(bool(degrees)), int(bool(clip_hillshade)),
             float(hillshade_azimuth), float(hillshade_altitude), float(hillshade_z_factor), planes, cols,
             ctypes.c_void_p(stream))
+    _lib.check(rc)
+    return out
+
+
+def _masks_and_slots(surface_attributes: Sequence[str], windowed_indexes: Sequence[str]) -> tuple[int, int, list[int]]:
+    surf_mask = 0
+    win_mask = 0
+    slots = []
+    for a in surface_attributes:
+        k = SURFACE_ORDER.index(a)
+        if surf_mask >> k & 1:
+            raise ValueError(f"duplicate attribute {a}")
+        surf_mask |= 1 << k
+        slots.append(k)
+    for a in windowed_indexes:
+        j = WINDOW_ORDER.index(a)
+        if win_mask >> j & 1:
+            raise ValueError(f"duplicate attribute {a}")
+        win_mask |= 1 << j
+        slots.append(10 + j)
+    return surf_mask, win_mask, slots
+
+
+def terrain_fused_host(
+    dem: np.ndarray,
+    resolution: float,
+    surface_attributes: Sequence[str] = (),
+    windowed_indexes: Sequence[str] = (),
+    surface_fit: str = "Florinsky",
+    curv_method: str = "geometric",
+    tri_method: str = "Riley",
+    window_size: int = 3,
+    degrees: bool = False,
+    clip_hillshade: bool = False,
+    hillshade_azimuth: float = 315.0,
+    hillshade_altitude: float = 45.0,
+    hillshade_z_factor: float = 1.0,
+    out: np.ndarray | None = None,
+    rows_per_block: int = 0,
+) -> np.ndarray:
+    """Host-buffer path (xb_terrain_fused_host): a C-contiguous float32/float64 NumPy raster is streamed through the GPU
+    in row blocks with halo rows (H2D / kernel / D2H overlapped); returns a (n_attr, H, W) NumPy array.  Pinned ``dem`` /
+    ``out`` buffers (e.g. views of torch pinned tensors) reach PCIe line rate; pageable ones work but copy slower."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("xdem_b200 needs a CUDA device (B200, sm_100a): no CPU fallback exists.")
+    if dem.ndim != 2 or dem.dtype not in (np.float32, np.float64):
+        raise ValueError("dem must be a 2-D float32/float64 array")
+    dem = np.ascontiguousarray(dem)
+    L = _lib.lib()
+    rows, cols = dem.shape
+    names = list(surface_attributes) + list(windowed_indexes)
+    if out is None:
+        out = np.empty((len(names), rows, cols), dtype=dem.dtype)
+    elif out.shape != (len(names), rows, cols) or out.dtype != dem.dtype or not out.flags.c_contiguous:
+        raise ValueError("bad `out` array")
+    surf_mask, win_mask, slots = _masks_and_slots(surface_attributes, windowed_indexes)
+    planes = (ctypes.c_void_p * N_PLANES)()
+    for i, slot in enumerate(slots):
+        planes[slot] = out[i].ctypes.data
+    with torch.cuda.device(torch.cuda.current_device()):
+        rc = L.xb_terrain_fused_host(
+            ctypes.c_void_p(dem.ctypes.data), 0 if dem.dtype == np.float32 else 1, rows, cols, float(resolution),
+            FIT_IDS[surface_fit.lower()], CURV_IDS[curv_method.lower()], surf_mask, win_mask, int(window_size),
+            0 if tri_method.lower() == "riley" else 1, int(bool(degrees)), int(bool(clip_hillshade)),
+            float(hillshade_azimuth), float(hillshade_altitude), float(hillshade_z_factor), planes,
+            int(rows_per_block))
     _lib.check(rc)
     return out

@@ -55,6 +55,6 @@ def launch_count() -> int:
 
 
 #: every symbol declared in include/xdem_b200.h (checked by tests/test_abi.py)
-EXPORTED = ["xb_last_error", "xb_version", "xb_launch_count", "xb_terrain_fused"]
+EXPORTED = ["xb_last_error", "xb_version", "xb_launch_count", "xb_terrain_fused", "xb_terrain_fused_host"]
 
 __all__ = ["lib", "check", "launch_count", "XdemB200Error", "LIB_PATH", "EXPORTED", "c_int32"]

@@ -50,14 +50,7 @@ int xb_num_sms(int* out) {
     return XB_OK;
 }
 
-extern "C" {
-#pragma GCC visibility push(default)
-
-const char* xb_last_error(void) { return g_err; }
-int xb_version(void) { return 100; }
-uint64_t xb_launch_count(void) { return g_launches.load(); }
-
-static int build_terrain_params(xbt::TerrainParams& p, int dtype, double resolution, int fit_id, int curv_method_id,
+int xb_build_terrain_params(xbt::TerrainParams& p, int dtype, double resolution, int fit_id, int curv_method_id,
                                 uint32_t surf_mask, uint32_t win_mask, int window_size, int tri_method_id, int degrees,
                                 int clip_hillshade, double az, double alt, double zf, int* hs_out, int* hw_out) {
     if (dtype != XB_F32 && dtype != XB_F64) {
@@ -119,7 +112,8 @@ static int build_terrain_params(xbt::TerrainParams& p, int dtype, double resolut
     } else {
         p.inv_d1 = 1.0 / (420 * r), p.inv_d2 = 1.0 / (35 * r * r), p.inv_d3 = 1.0 / (100 * r * r);
     }
-    p.rad2deg = 180.0 / M_PI;
+    // np.rad2deg on a float32 array multiplies by the float32 constant 180.0f/pi_f (terrain.py:591)
+    p.rad2deg = dtype == XB_F32 ? (double)(180.0f / 3.14159265358979323846f) : 180.0 / M_PI;
     // surfit.py:614-615
     const double az_rad = (360.0 - az) * (M_PI / 180.0);
     const double alt_rad = alt * (M_PI / 180.0);
@@ -147,6 +141,14 @@ static int build_terrain_params(xbt::TerrainParams& p, int dtype, double resolut
     return XB_OK;
 }
 
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char* xb_last_error(void) { return g_err; }
+int xb_version(void) { return 100; }
+uint64_t xb_launch_count(void) { return g_launches.load(); }
+
 int xb_terrain_fused(const void* dem_dev, int dtype, int64_t rows_buf, int64_t cols, int64_t ld, int64_t row_begin,
                      int64_t row_end, double resolution, int fit_id, int curv_method_id, uint32_t surf_mask,
                      uint32_t win_mask, int window_size, int tri_method_id, int degrees, int clip_hillshade,
@@ -165,7 +167,7 @@ int xb_terrain_fused(const void* dem_dev, int dtype, int64_t rows_buf, int64_t c
     xbt::TerrainParams p;
     memset(&p, 0, sizeof(p));
     int hs = 0, hw = 0;
-    int rc = build_terrain_params(p, dtype, resolution, fit_id, curv_method_id, surf_mask, win_mask, window_size,
+    int rc = xb_build_terrain_params(p, dtype, resolution, fit_id, curv_method_id, surf_mask, win_mask, window_size,
                                   tri_method_id, degrees, clip_hillshade, hillshade_azimuth, hillshade_altitude,
                                   hillshade_z_factor, &hs, &hw);
     if (rc) return rc;

@@ -21,6 +21,7 @@
 // windowed indexes use un-contracted IEEE fp32 ops in the reference's (row-major, sequential) order so that
 // integer-valued DEMs are bit-exact.
 #include "xb_common.cuh"
+#include "xb_math.cuh"
 #include "xb_terrain.cuh"
 
 #include <math_constants.h>
@@ -55,11 +56,17 @@ struct Num<double> {
     static __device__ __forceinline__ double nan() { return CUDART_NAN; }
 };
 
-__device__ __forceinline__ float xb_atan(float x) { return atanf(x); }
-__device__ __forceinline__ double xb_atan(double x) { return atan(x); }
-__device__ __forceinline__ float xb_atan2(float y, float x) { return atan2f(y, x); }
-__device__ __forceinline__ double xb_atan2(double y, double x) { return atan2(y, x); }
-__device__ __forceinline__ float xb_rsqrt(float x) { return rsqrtf(x); }
+// slope [rad] from the squared gradient norm: atan(sqrt(g2))  (surfit.py:592)
+__device__ __forceinline__ float slope_rad(float g2) { return xbm::atan_pos(xbm::sqrt_fast(g2)); }
+__device__ __forceinline__ double slope_rad(double g2) { return atan(sqrt(g2)); }
+// aspect [rad]: (-arctan2(-zx, zy)) mod 2*pi  (surfit.py:600)
+__device__ __forceinline__ float aspect_rad(float zx, float zy) { return xbm::aspect_angle(zx, zy); }
+__device__ __forceinline__ double aspect_rad(double zx, double zy) {
+    double a = -atan2(-zx, zy);
+    if (a < 0.0) a += 6.283185307179586;
+    return a;
+}
+__device__ __forceinline__ float xb_rsqrt(float x) { return xbm::rsqrt_approx(x); }
 __device__ __forceinline__ double xb_rsqrt(double x) { return 1.0 / sqrt(x); }
 __device__ __forceinline__ float xb_fma(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double xb_fma(double a, double b, double c) { return fma(a, b, c); }
@@ -76,15 +83,14 @@ __device__ __forceinline__ void store_vec4(double* p, const double (&v)[4]) {
 }
 
 template <typename T>
-__device__ __forceinline__ void store4(void* plane, long long ld, long long y, long long x, long long W, bool vec_ok,
-                                       const T (&v)[4]) {
-    T* p = reinterpret_cast<T*>(plane) + y * ld + x;
-    if (vec_ok && x + 3 < W) {
+__device__ __forceinline__ void store4(void* plane, long long off, bool full, int nvalid, const T (&v)[4]) {
+    T* p = reinterpret_cast<T*>(plane) + off;
+    if (full) {
         store_vec4(p, v);
     } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (x + k < W) __stcs(p + k, v[k]);
+            if (k < nvalid) __stcs(p + k, v[k]);
     }
 }
 
@@ -217,8 +223,8 @@ __device__ __forceinline__ Derivs<T> derivs_at(const T (&win)[2 * H + 1][4 + 2 *
 // ---------------------------------------------------------------------------------------------------------------
 // Kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int HS, int HW, int RPW, bool USE_TMA>
-__global__ void __launch_bounds__(NTHREADS, 2)
+template <typename T, int HS, int HW, int RPW, bool USE_TMA, bool ALG>
+__global__ void __launch_bounds__(NTHREADS, ALG ? 2 : 3)
 terrain_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TerrainParams p) {
     constexpr int H = (HS > HW) ? HS : HW;
     constexpr int TH = NWARPS * RPW;
@@ -263,7 +269,7 @@ terrain_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     const bool need_surf = p.surf_mask != 0;
     const bool need2 = (p.surf_mask & ~7u) != 0;
     const bool need_sah = (p.surf_mask & 7u) != 0;
-    const bool need_curv_alg = (p.surf_mask & ~15u) != 0;
+    const bool need_curv_alg = ALG && (p.surf_mask & ~15u) != 0;  // ALG=false kernels carry no FP64 algebra
     const bool vec_ok = p.vec_ok != 0;
 
     int it = 0;
@@ -289,12 +295,14 @@ terrain_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         }
 
         const long long x0 = x_tile + 4 * lane;
+        const bool full = vec_ok && (x0 + 3 < W);
+        const int nvalid = (int)((W - x0) < 4 ? (W - x0) : 4);
 #pragma unroll 1
         for (int rr = 0; rr < RPW; ++rr) {
             const int ly = warp * RPW + rr;  // row inside the tile
             const long long y = y_tile + ly;
             if (y >= p.row_end || x0 >= W) continue;  // warp-uniform in y; lanes past the raster edge idle
-            const long long yo = y - p.row_begin;
+            const long long off = (y - p.row_begin) * p.out_ld + x0;
 
             T win[2 * H + 1][4 + 2 * H];
 #pragma unroll
@@ -312,38 +320,42 @@ terrain_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                         sx[k] = d.sx, sy[k] = d.sy, sxx[k] = d.sxx, syy[k] = d.syy, sxy[k] = d.sxy, car[k] = d.carrier;
                     }
                     if (need_sah) {
-                        T slope[4], aspect[4], hs[4];
+                        T zx[4], zy[4], g2[4];
                         const T inv1 = (T)p.inv_d1;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const T zx = sx[k] * inv1, zy = sy[k] * inv1;
-                            const T g2 = xb_fma(zx, zx, zy * zy);
-                            if (p.surf_mask & 1u) {
-                                T s = xb_atan(Num<T>::sqrt(g2));  // surfit.py:592
-                                if (p.degrees) s = s * (T)p.rad2deg;
-                                slope[k] = s + car[k];
-                            }
-                            if (p.surf_mask & 2u) {
-                                // (-arctan2(-zx, zy)) mod 2*pi  (surfit.py:600)
-                                T a = -xb_atan2(-zx, zy);
-                                if (a < T(0)) a = (T)((double)a + 6.283185307179586);
-                                if (p.degrees) a = a * (T)p.rad2deg;
-                                aspect[k] = a + car[k];
-                            }
-                            if (p.surf_mask & 4u) {
-                                // 1.5 + 254*(sin(alt) cos(s') + cos(alt) sin(s') sin(az - aspect)), s' = atan(zf*|grad|)
-                                // evaluated algebraically (surfit.py:606-622): cos(s') = 1/sqrt(1+zf^2 g2),
-                                // sin(s') sin(az-asp) = zf (sin(az) zy - cos(az) zx) / sqrt(1+zf^2 g2)
-                                const T r = xb_rsqrt(xb_fma((T)p.zf2, g2, T(1)));
-                                const T inner = xb_fma((T)p.hs_ky, zy, xb_fma(-(T)p.hs_kx, zx, (T)p.hs_sin_alt));
-                                T h = xb_fma(T(254) * r, inner, T(1.5));
-                                if (p.clip_hs) h = fmin(fmax(h, T(0)), T(255));  // NaN handled by the carrier
-                                hs[k] = h + car[k];
-                            }
+                            zx[k] = sx[k] * inv1, zy[k] = sy[k] * inv1;
+                            g2[k] = xb_fma(zx[k], zx[k], zy[k] * zy[k]);
                         }
-                        if (p.surf_mask & 1u) store4<T>(p.out[0], p.out_ld, yo, x0, W, vec_ok, slope);
-                        if (p.surf_mask & 2u) store4<T>(p.out[1], p.out_ld, yo, x0, W, vec_ok, aspect);
-                        if (p.surf_mask & 4u) store4<T>(p.out[2], p.out_ld, yo, x0, W, vec_ok, hs);
+                        const T ang = p.degrees ? (T)p.rad2deg : T(1);
+                        if (p.surf_mask & 1u) {
+                            T o[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) o[k] = slope_rad(g2[k]) * ang + car[k];  // surfit.py:592
+                            store4<T>(p.out[0], off, full, nvalid, o);
+                        }
+                        if (p.surf_mask & 2u) {
+                            T o[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) o[k] = aspect_rad(zx[k], zy[k]) * ang + car[k];  // surfit.py:600
+                            store4<T>(p.out[1], off, full, nvalid, o);
+                        }
+                        if (p.surf_mask & 4u) {
+                            // 1.5 + 254*(sin(alt) cos(s') + cos(alt) sin(s') sin(az - aspect)), s' = atan(zf*|grad|),
+                            // evaluated algebraically (surfit.py:606-622): cos(s') = 1/sqrt(1+zf^2 g2),
+                            // sin(s') sin(az-asp) = zf (sin(az) zy - cos(az) zx) / sqrt(1+zf^2 g2)
+                            T o[4];
+                            const T ky = (T)p.hs_ky, kx = -(T)p.hs_kx, sa = (T)p.hs_sin_alt, zf2 = (T)p.zf2;
+                            const T lo = p.clip_hs ? T(0) : -CUDART_INF_F, hi = p.clip_hs ? T(255) : CUDART_INF_F;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const T r = xb_rsqrt(xb_fma(zf2, g2[k], T(1)));
+                                const T inner = xb_fma(ky, zy[k], xb_fma(kx, zx[k], sa));
+                                const T h = xb_fma(T(254) * r, inner, T(1.5));
+                                o[k] = fmin(fmax(h, lo), hi) + car[k];  // clip (terrain.py:596); NaN via the carrier
+                            }
+                            store4<T>(p.out[2], off, full, nvalid, o);
+                        }
                     }
                     if (p.surf_mask & 8u) {
                         // curvature = -2 (z_xx + z_yy) * 100 (surfit.py:636); z_xx, z_yy share their divider
@@ -351,9 +363,9 @@ terrain_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                         const T f = (T)(-200.0 * p.inv_d2);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) cv[k] = (sxx[k] + syy[k]) * f + car[k];
-                        store4<T>(p.out[3], p.out_ld, yo, x0, W, vec_ok, cv);
+                        store4<T>(p.out[3], off, full, nvalid, cv);
                     }
-                    if (need_curv_alg) {
+                    if constexpr (ALG) if (need_curv_alg) {
                         // Cancellation-prone algebra in FP64 (surfit.py:638-943), from the exact unscaled sums
                         T o4[4], o5[4], o6[4], o7[4], o8[4], o9[4];
 #pragma unroll
@@ -409,12 +421,12 @@ terrain_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                                 o9[k] = (T)((flat0 ? 0.0 : vmin) * 100.0 + carr);
                             }
                         }
-                        if (p.surf_mask & (1u << 4)) store4<T>(p.out[4], p.out_ld, yo, x0, W, vec_ok, o4);
-                        if (p.surf_mask & (1u << 5)) store4<T>(p.out[5], p.out_ld, yo, x0, W, vec_ok, o5);
-                        if (p.surf_mask & (1u << 6)) store4<T>(p.out[6], p.out_ld, yo, x0, W, vec_ok, o6);
-                        if (p.surf_mask & (1u << 7)) store4<T>(p.out[7], p.out_ld, yo, x0, W, vec_ok, o7);
-                        if (p.surf_mask & (1u << 8)) store4<T>(p.out[8], p.out_ld, yo, x0, W, vec_ok, o8);
-                        if (p.surf_mask & (1u << 9)) store4<T>(p.out[9], p.out_ld, yo, x0, W, vec_ok, o9);
+                        if (p.surf_mask & (1u << 4)) store4<T>(p.out[4], off, full, nvalid, o4);
+                        if (p.surf_mask & (1u << 5)) store4<T>(p.out[5], off, full, nvalid, o5);
+                        if (p.surf_mask & (1u << 6)) store4<T>(p.out[6], off, full, nvalid, o6);
+                        if (p.surf_mask & (1u << 7)) store4<T>(p.out[7], off, full, nvalid, o7);
+                        if (p.surf_mask & (1u << 8)) store4<T>(p.out[8], off, full, nvalid, o8);
+                        if (p.surf_mask & (1u << 9)) store4<T>(p.out[9], off, full, nvalid, o9);
                     }
                 }
             }
@@ -523,11 +535,11 @@ terrain_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                             }
                         }
                     }
-                    if (p.win_mask & 1u) store4<T>(p.out[10], p.out_ld, yo, x0, W, vec_ok, tpi);
-                    if (p.win_mask & 2u) store4<T>(p.out[11], p.out_ld, yo, x0, W, vec_ok, tri);
-                    if (p.win_mask & 4u) store4<T>(p.out[12], p.out_ld, yo, x0, W, vec_ok, rough);
+                    if (p.win_mask & 1u) store4<T>(p.out[10], off, full, nvalid, tpi);
+                    if (p.win_mask & 2u) store4<T>(p.out[11], off, full, nvalid, tri);
+                    if (p.win_mask & 4u) store4<T>(p.out[12], off, full, nvalid, rough);
                     if constexpr (HW == 1) {
-                        if (p.win_mask & 8u) store4<T>(p.out[13], p.out_ld, yo, x0, W, vec_ok, rug);
+                        if (p.win_mask & 8u) store4<T>(p.out[13], off, full, nvalid, rug);
                     }
                 }
             }
@@ -550,13 +562,13 @@ terrain_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 // ---------------------------------------------------------------------------------------------------------------
 // Host-side launch
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int HS, int HW, int RPW, bool USE_TMA>
+template <typename T, int HS, int HW, int RPW, bool USE_TMA, bool ALG>
 static int launch_cfg(const CUtensorMap& tmap, const TerrainParams& p, int num_sms, cudaStream_t stream) {
     constexpr int H = (HS > HW) ? HS : HW;
     constexpr int TH = NWARPS * RPW;
     constexpr int BOXH = TH + 2 * H;
     const size_t smem = (size_t)(USE_TMA ? NSTAGES : 1) * (((size_t)BOXW * BOXH * sizeof(T) + 127) / 128 * 128);
-    auto kern = terrain_fused_kernel<T, HS, HW, RPW, USE_TMA>;
+    auto kern = terrain_fused_kernel<T, HS, HW, RPW, USE_TMA, ALG>;
     XB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     XB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTHREADS, smem));
@@ -572,8 +584,15 @@ template <typename T, int HS, int HW>
 static int launch_tma_sel(bool use_tma, const CUtensorMap& tmap, const TerrainParams& p, int num_sms,
                           cudaStream_t stream) {
     constexpr int RPW = 8;
-    if (use_tma) return launch_cfg<T, HS, HW, RPW, true>(tmap, p, num_sms, stream);
-    return launch_cfg<T, HS, HW, RPW, false>(tmap, p, num_sms, stream);
+    const bool alg = HS > 0 && (p.surf_mask & ~15u) != 0;
+    if constexpr (HS > 0) {
+        if (alg) {
+            if (use_tma) return launch_cfg<T, HS, HW, RPW, true, true>(tmap, p, num_sms, stream);
+            return launch_cfg<T, HS, HW, RPW, false, true>(tmap, p, num_sms, stream);
+        }
+    }
+    if (use_tma) return launch_cfg<T, HS, HW, RPW, true, false>(tmap, p, num_sms, stream);
+    return launch_cfg<T, HS, HW, RPW, false, false>(tmap, p, num_sms, stream);
 }
 
 template <typename T>

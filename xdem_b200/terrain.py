@@ -199,16 +199,31 @@ def _get_terrain_attribute(
         pass
 
     is_raster = _arrays.is_raster_like(dem)
-    t, kind = _arrays.to_device(dem)
     uniq_surf = list(dict.fromkeys(surf))
     uniq_win = list(dict.fromkeys(win))
-    planes = _engine.terrain_fused(
-        t, float(resolution), surface_attributes=uniq_surf, windowed_indexes=uniq_win, surface_fit=surface_fit,
-        curv_method=curv_method, tri_method=tri_method, window_size=window_size, degrees=degrees,
-        clip_hillshade=True, hillshade_azimuth=hillshade_azimuth, hillshade_altitude=hillshade_altitude,
-        hillshade_z_factor=hillshade_z_factor)
     index = {a: i for i, a in enumerate(uniq_surf + uniq_win)}
-    outs = [_arrays.from_device(planes[index[a]], kind, out_dtype) for a in attribute]
+    kwargs = dict(surface_attributes=uniq_surf, windowed_indexes=uniq_win, surface_fit=surface_fit,
+                  curv_method=curv_method, tri_method=tri_method, window_size=window_size, degrees=degrees,
+                  clip_hillshade=True, hillshade_azimuth=hillshade_azimuth, hillshade_altitude=hillshade_altitude,
+                  hillshade_z_factor=hillshade_z_factor)
+    if isinstance(dem, torch.Tensor) and dem.is_cuda:
+        # device-resident raster: one launch, CUDA tensors out
+        t, kind = _arrays.to_device(dem)
+        planes = _engine.terrain_fused(t, float(resolution), **kwargs)
+        outs = [_arrays.from_device(planes[index[a]], kind, out_dtype) for a in attribute]
+    else:
+        # host raster (ndarray / masked array / Raster / CPU tensor): streamed through the GPU in row blocks
+        as_tensor = isinstance(dem, torch.Tensor)
+        arr = dem.numpy() if as_tensor else _arrays.to_host_nan_array(dem)
+        if arr.dtype not in (np.float32, np.float64):
+            arr = arr.astype(np.float32)
+        planes_h = _engine.terrain_fused_host(arr, float(resolution), **kwargs)
+        outs = []
+        for a in attribute:
+            o = planes_h[index[a]]
+            if out_dtype is not None and o.dtype != np.dtype(out_dtype):
+                o = o.astype(out_dtype)
+            outs.append(torch.from_numpy(o) if as_tensor else o)
 
     if is_raster:
         try:
