@@ -89,6 +89,70 @@ int xb_terrain_fused_host(const void* dem_host, int dtype, int64_t rows, int64_t
                           double hillshade_altitude, double hillshade_z_factor, void* const* out_planes_host,
                           int64_t rows_per_block);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Empirical variogram: all-pairs distance / squared-difference lag binning.
+ * Replaces what skgstat.Variogram (third-party; scikit-gstat>=1.0.18, setup.cfg:56) computes for
+ * xdem.spatialstats._get_pdist_empirical_variogram (spatialstats.py:1064-1101): for every sample pair i<j the lag class
+ * k with edge2[k-1] <= d2 < edge2[k] (d2 = squared pixel distance; edge2 = integer thresholds the host derives from the
+ * float64 right bin edges), count[k] += 1, sumsq[k] += (v_i - v_j)^2 (Matheron numerator).  Pairs with
+ * d2 >= edge2[n_bins-1] are dropped (skgstat: distances beyond maxlag).
+ *
+ *  pts_dev      int32 [n_groups*G][4] = (col, row, float32 value bits, sorted index or -1 for padding); samples sorted
+ *               along a space-filling curve and cut into groups of G = xb_variogram_group_size() samples
+ *  gbox_dev     int32 [n_groups][4] bounding box (xmin, ymin, xmax, ymax) of the valid samples of each group
+ *  edge2_dev    uint64 [n_bins] ascending thresholds
+ *  unit_prefix_dev  int64 [n_groups+1]: work units are (group i, chunk of xb_variogram_chunk() j-groups >= i);
+ *               unit_prefix[i] = number of units of rows < i.  [unit_begin, unit_end) is this call's share of the units
+ *               (multi-GPU: ranks take disjoint ranges and all-reduce count/sumsq, 2*n_bins*8 bytes)
+ *  wide         0: d2 fits 32 bits (raster diagonal^2 < 2^32), 1: 64-bit distances
+ *  count_dev    uint64 [n_bins] and sumsq_dev double [n_bins], accumulated into (caller zeroes them)
+ */
+int xb_variogram_group_size(void);
+int xb_variogram_chunk(void);
+int xb_variogram_pairs(const int32_t* pts_dev, const int32_t* gbox_dev, int64_t n_groups,
+                       const unsigned long long* edge2_dev, int n_bins, const int64_t* unit_prefix_dev,
+                       int64_t unit_begin, int64_t unit_end, int wide, unsigned long long* count_dev,
+                       double* sumsq_dev, void* stream);
+/* Largest squared pixel distance over all sample pairs, accumulated with max into maxd2_dev[0] (skgstat's "even"
+ * binning clips maxlag to the largest sampled distance). */
+int xb_variogram_maxd2(const int32_t* pts_dev, const int32_t* gbox_dev, int64_t n_groups,
+                       unsigned long long* maxd2_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Nuth & Kaab (2011) inner step.
+ * xb_nk_aux replaces `_nuth_kaab_aux_vars` + the zero-slope mask (affine.py:412-474, 578-579): np.gradient semantics
+ * (unit spacing, one-sided at raster borders), slope_tan = sqrt(gx^2+gy^2), aspect = arctan2(-gx,gy)+pi, all float32.
+ * The buffer may be a row shard: top_is_border / bottom_is_border say whether buffer row 0 / rows_buf-1 are raster
+ * borders (otherwise they are halo rows and must lie outside [row_begin,row_end)).
+ */
+int xb_nk_aux(const float* ref_dev, int64_t rows_buf, int64_t cols, int64_t ld, int top_is_border,
+              int bottom_is_border, int64_t row_begin, int64_t row_end, float* slope_tan_dev, float* aspect_dev,
+              int64_t out_ld, void* stream);
+
+/* dh = ref - bilinear(tba at (row + dy_px, col + dx_px)) where sub_mask != 0, NaN elsewhere (affine.py:179-184;
+ * geoutils `_interp_points`, linear, NaN-propagating -- restated).  dh / sub_mask / aspect are
+ * contiguous rows x cols; tba_dev is a buffer of tba_rows_total rows whose row `tba_row0` is raster row 0 of this
+ * shard (halo rows above/below for row shards).  asp_minmax_dev[0/1] receive min/max (float32 bit patterns) of aspect
+ * over finite dh (caller initialises to 0xffffffff / 0), n_finite_dev[0] the finite count (accumulated). */
+int xb_nk_dh(const float* ref_dev, const float* tba_dev, const uint8_t* sub_mask_dev, const float* aspect_dev,
+             int64_t rows, int64_t cols, int64_t ld, int64_t tba_ld, int64_t tba_row0, int64_t tba_rows_total,
+             double dx_px, double dy_px, float* dh_dev, uint32_t* asp_minmax_dev, unsigned long long* n_finite_dev,
+             void* stream);
+
+/* One MSD radix-select histogram pass over order-preserving float32 keys (exact medians: np.nanmedian(dh),
+ * affine.py:504, and the per-aspect-bin nanmedian of y = (dh - vshift)/slope_tan, base.py:1014-1020).
+ * mode 0: key = dh, n_groups = 1.  mode 1: key = float32(y), group = aspect bin among n_groups equal-width bins of
+ * [asp_lo, asp_hi] (scipy.stats.binned_statistic semantics).  For keys with (key & prefix_mask) == prefix_dev[group]:
+ * hist_dev[group*n_digits + ((key >> shift) & (n_digits-1))] += 1.  moments_dev (or NULL): [n, sum y, sum y^2]. */
+int xb_nk_hist(const float* dh_dev, const float* slope_tan_dev, const float* aspect_dev, int64_t n, int mode,
+               double vshift, double asp_lo, double asp_hi, int n_groups, const uint32_t* prefix_dev,
+               uint32_t prefix_mask, int shift, int n_digits, unsigned long long* hist_dev, double* moments_dev,
+               void* stream);
+/* next_key_dev[group] = min(next_key_dev[group], smallest key > sel_dev[group]) -- upper median of even-sized groups. */
+int xb_nk_next(const float* dh_dev, const float* slope_tan_dev, const float* aspect_dev, int64_t n, int mode,
+               double vshift, double asp_lo, double asp_hi, int n_groups, const uint32_t* sel_dev,
+               uint32_t* next_key_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

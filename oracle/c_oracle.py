@@ -69,3 +69,21 @@ def windowed_indexes(dem: np.ndarray, window_size: int, attrs: list[str], tri_me
                                int(nthreads))
     assert rc == 0
     return out
+
+
+def variogram_pairs(coords: np.ndarray, values: np.ndarray, edges: np.ndarray, nthreads: int = 0
+                    ) -> tuple[np.ndarray, np.ndarray, float]:
+    """All-pairs lag binning (C/OpenMP): returns (count[int64], sumsq[float64], dmax)."""
+    x = np.ascontiguousarray(coords[:, 0], dtype=np.float64)
+    y = np.ascontiguousarray(coords[:, 1], dtype=np.float64)
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    e = np.ascontiguousarray(edges, dtype=np.float64)
+    count = np.zeros(len(e), dtype=np.int64)
+    sumsq = np.zeros(len(e), dtype=np.float64)
+    dmax = ctypes.c_double(0.0)
+    rc = lib().xo_variogram_pairs(ctypes.c_void_p(x.ctypes.data), ctypes.c_void_p(y.ctypes.data),
+                                  ctypes.c_void_p(v.ctypes.data), ctypes.c_int64(len(v)),
+                                  ctypes.c_void_p(e.ctypes.data), int(len(e)), ctypes.c_void_p(count.ctypes.data),
+                                  ctypes.c_void_p(sumsq.ctypes.data), ctypes.byref(dmax), int(nthreads))
+    assert rc == 0
+    return count, sumsq, float(dmax.value)

@@ -80,6 +80,37 @@ def main() -> None:
         store[f"win|fractal64|scipy|3|Riley|{a}"] = o
     np.savez_compressed(os.path.join(OUT, "terrain_reference.npz"), **store)
     print(f"terrain_reference.npz: {len(store)} arrays")
+    nk_golden(ref)
+
+
+def nk_golden(ref) -> None:  # noqa
+    """Per-iteration outputs of the reference's own Nuth-Kaab code (affine.py:102-147, 477-609) on a synthetic pair."""
+    import scipy.optimize
+
+    A = ref.coreg_affine
+    r, t = synth.nk_pair((240, 300))
+    r[50:54, 60:70] = np.nan
+    t[100, 100] = np.nan
+    t[180:183, 20:25] = np.nan
+    transform = ref.Affine(5.0, 0, 1000.0, 0, -5.0, 9000.0)
+    inl = np.ones(r.shape, bool)
+    inl[200:210, 250:260] = False
+
+    class CRS:
+        is_projected = True
+
+    pf = {"fit_or_bin": "bin_and_fit", "fit_optimizer": scipy.optimize.curve_fit, "bin_sizes": 72,
+          "bin_statistic": np.nanmedian, "fit_func": None, "nd": 1, "bias_var_names": ["aspect"]}
+    pr = {"subsample": 1.0, "random_state": None}
+    offs = []
+    for n_it in range(1, 7):
+        out, nfin = A.nuth_kaab(r.copy(), t.copy(), inl, transform, CRS(), "Area", 0.0, n_it, dict(pf), pr, "z")
+        offs.append([float(v) for v in out])
+    st, asp = A._nuth_kaab_aux_vars(r, t)
+    np.savez_compressed(os.path.join(OUT, "nk_reference.npz"), ref=r, tba=t, inlier=inl,
+                        offsets=np.array(offs), n_valid=np.array(nfin), slope_tan=st, aspect=asp,
+                        transform=np.array([5.0, 0, 1000.0, 0, -5.0, 9000.0]))
+    print("nk_reference.npz:", offs[-1], nfin)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,199 @@
+"""GPU parity tests of the variogram (K2) and Nuth-Kaab (K3) kernels through the public API -> C ABI."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------------- variogram
+
+
+def _sample(shape, n, seed, nan_frac=0.0):
+    rng = np.random.default_rng(seed)
+    vals = rng.normal(size=shape).astype(np.float32)
+    if nan_frac:
+        vals.ravel()[rng.choice(vals.size, int(nan_frac * vals.size), replace=False)] = np.nan
+    finite = np.flatnonzero(np.isfinite(vals.ravel()))
+    idx = rng.choice(finite, n, replace=False)
+    return vals, idx
+
+
+@pytest.mark.parametrize("shape,n,gsd", [((300, 300), 3000, 5.0), ((257, 257), 1000, 1.0), ((90, 90), 129, 30.0),
+                                         ((64, 64), 128, 0.5), ((40, 40), 5, 2.0)])
+@pytest.mark.parametrize("bins", ["even", "default"])
+def test_pairwise_binning_vs_oracle(shape, n, gsd, bins) -> None:
+    """Counts bit-exact, Matheron sums within 1e-5 relative of the float64 oracle (restated scikit-gstat)."""
+    import torch
+
+    from oracle import variogram_oracle as vo
+    from xdem_b200 import spatialstats as xs
+
+    vals, idx = _sample(shape, n, 44)
+    nx, ny = shape
+    coords = vo.grid_coords(shape, gsd)  # reference glue: coords[k] for flat sample k
+    maxlag = float(np.hypot((nx - 1) * gsd, (ny - 1) * gsd))
+    flat = vals.ravel()
+    if bins == "even":
+        b_o, exp_o, cnt_o = vo.empirical_variogram(coords[idx], flat[idx], "even", n_lags=50, maxlag=maxlag)
+        edges_in = None
+    else:
+        edges_in = np.asarray(vo.default_bins(gsd, maxlag))
+        b_o, exp_o, cnt_o = vo.empirical_variogram(coords[idx], flat[idx], edges_in)
+    ti = torch.from_numpy(idx).cuda()
+    x, y = ti % nx, ti // nx
+    v = torch.from_numpy(flat).cuda()[ti]
+    edges, cnt, ssq = xs.pairwise_lag_binning(x, y, v, edges_in, gsd, n_lags=50, maxlag=maxlag)
+    assert np.array_equal(edges, b_o)
+    assert np.array_equal(cnt, cnt_o), (cnt - cnt_o)
+    with np.errstate(all="ignore"):
+        exp = np.where(cnt > 0, ssq / (2.0 * cnt), np.nan)
+    assert np.allclose(exp, exp_o, rtol=1e-5, equal_nan=True)
+
+
+def test_sample_empirical_variogram_frame() -> None:
+    """Public API: frame layout of spatialstats.py:1512-1546 (last bin dropped, dtypes) + oracle values."""
+    from oracle import variogram_oracle as vo
+    from xdem_b200 import spatialstats as xs
+
+    vals, _ = _sample((200, 200), 10, 3, nan_frac=0.01)
+    df = xs.sample_empirical_variogram(vals, gsd=5.0, subsample=1500, subsample_method="pdist_point", random_state=7)
+    assert list(df.columns) == ["exp", "lags", "count", "err_exp"]
+    assert df["count"].dtype == np.int64 and df["exp"].dtype == np.float64 and df["lags"].dtype == np.float64
+    edges = vo.default_bins(5.0, float(np.hypot(199 * 5.0, 199 * 5.0)))
+    assert len(df) == len(edges) - 1 and np.allclose(df["lags"].values, edges[:-1])
+    assert df["err_exp"].isna().all()
+    # several runs: aggregated mean / std / summed counts
+    df3 = xs.sample_empirical_variogram(vals, gsd=5.0, subsample=400, subsample_method="pdist_point", n_variograms=3,
+                                        random_state=7, bin_func="even", n_lags=20)
+    assert len(df3) >= 19 and (df3["count"] > 0).any()
+    with pytest.raises(NotImplementedError):
+        xs.sample_empirical_variogram(vals, gsd=5.0, subsample=100)  # default cdist_equidistant sampler
+    with pytest.raises(ValueError, match="ground sampling distance must be defined"):
+        xs.sample_empirical_variogram(vals, subsample=100, subsample_method="pdist_point")
+
+
+def test_variogram_large_properties() -> None:
+    """Size-independent properties at N = 2e5 (2e10 pairs): every pair lands in exactly one class (sum of counts ==
+    N(N-1)/2 with a last edge beyond the extent), the result does not depend on sample order, and a constant field has
+    zero semivariance."""
+    import torch
+
+    from xdem_b200 import spatialstats as xs
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    N, S = 200_000, 20000
+    lin = torch.randperm(S * S // 1000, generator=g, device="cuda")[:N].to(torch.int64) * 1000 + 7
+    x, y = lin % S, lin // S
+    v = torch.randn(N, generator=g, device="cuda")
+    edges = np.linspace(0, 1.5 * S * 5.0, 41)[1:]
+    e, cnt, ssq = xs.pairwise_lag_binning(x, y, v, edges, 5.0)
+    assert int(cnt.sum()) == N * (N - 1) // 2
+    perm = torch.randperm(N, generator=g, device="cuda")
+    e2, cnt2, ssq2 = xs.pairwise_lag_binning(x[perm], y[perm], v[perm], edges, 5.0)
+    assert np.array_equal(cnt, cnt2) and np.allclose(ssq, ssq2, rtol=1e-6)
+    _, cnt3, ssq3 = xs.pairwise_lag_binning(x, y, torch.full_like(v, 3.25), edges, 5.0)
+    assert np.array_equal(cnt3, cnt) and np.all(ssq3 == 0)
+    # white noise: semivariance ~ variance (=1) in every populated class
+    with np.errstate(all="ignore"):
+        gamma = ssq / (2.0 * cnt)
+    assert np.allclose(gamma[cnt > 1e6], 1.0, atol=0.02)
+
+
+# ------------------------------------------------------------------------------------------------- Nuth & Kaab
+
+
+def test_nk_aux_bit_exact() -> None:
+    import torch
+
+    from xdem_b200 import coreg
+
+    g = parity.load_golden("nk_reference.npz")
+    st = coreg._NKState(torch.from_numpy(g["ref"]).cuda(), torch.from_numpy(g["tba"]).cuda(), None)
+    ref_st = g["slope_tan"].copy()
+    ref_st[np.isclose(ref_st, 0)] = np.nan
+    assert np.array_equal(st.slope_tan.cpu().numpy(), ref_st, equal_nan=True)  # IEEE ops in NumPy's order
+    asp = st.aspect.cpu().numpy()
+    assert parity.nanmask_equal(asp, g["aspect"])
+    assert np.nanmax(np.abs(asp - g["aspect"])) <= 4 * np.spacing(np.float32(6.3))  # atan2f: a few ulp
+
+
+def test_nk_step_pieces_vs_oracle() -> None:
+    """dh, its exact median, the per-bin medians / counts and p0 of one iteration against the oracle."""
+    import torch
+
+    from oracle import nk_oracle as nk
+    from xdem_b200 import coreg
+
+    g = parity.load_golden("nk_reference.npz")
+    ref, tba, inl = g["ref"], g["tba"], g["inlier"]
+    a_e = (5.0, -5.0)
+    slope_tan, aspect = nk.aux_vars(ref)
+    valid = np.isfinite(ref) & np.isfinite(tba) & np.isfinite(slope_tan) & np.isfinite(aspect) & inl
+    st = coreg._NKState(torch.from_numpy(ref).cuda(), torch.from_numpy(tba).cuda(), torch.from_numpy(inl).cuda())
+    assert np.array_equal(st.valid.cpu().numpy(), valid)
+    for offs in ((0.0, 0.0), (1.85, 3.05), (-7.3, 12.9), (5.0, -10.0)):
+        dx, dy = offs[0] / a_e[0], offs[1] / a_e[1]
+        lo, hi, n_fin = st.compute_dh(dx, dy)
+        dh_o = nk.dh_at(ref, tba, valid, dx, dy)
+        dh_g = st.dh.cpu().numpy().reshape(ref.shape)[valid]
+        assert np.array_equal(np.isnan(dh_g), np.isnan(dh_o)), offs
+        assert n_fin == int(np.isfinite(dh_o).sum())
+        m = np.isfinite(dh_o)
+        assert np.allclose(dh_g[m], dh_o[m], rtol=0, atol=2e-4)  # float32 storage of values ~1e3 apart
+        med, cnt, _ = st.select_medians(0, 0.0, 0.0, 1.0, 1)
+        assert cnt[0] == n_fin
+        assert med[0] == pytest.approx(float(np.median(dh_g[m].astype(np.float64))), rel=0, abs=0)  # exact select
+        assert med[0] == pytest.approx(float(np.nanmedian(dh_o)), abs=2e-4)
+        # aspect range over finite dh
+        asp_v = aspect[valid][m]
+        assert lo == float(asp_v.min()) and hi == float(asp_v.max())
+        # per-bin medians of y
+        _, _, dbg = nk.iteration_step((offs[0], offs[1], 0.0), ref, tba, valid, slope_tan, aspect, a_e)
+        med_b, cnt_b, mom = st.select_medians(1, dbg["vshift"], lo, hi, 72, want_moments=True)
+        assert np.array_equal(cnt_b, dbg["count"].astype(np.int64)), offs
+        assert np.allclose(med_b, dbg["median"], rtol=2e-4, atol=2e-4, equal_nan=True)
+        n, s1, s2 = mom
+        assert n == cnt_b.sum()
+        assert s1 / n == pytest.approx(dbg["p0"][2], rel=1e-3, abs=1e-3)
+
+
+def test_nk_full_fit_vs_reference_fixture() -> None:
+    """Whole fit against the per-iteration outputs of the reference's own code (tests/golden/nk_reference.npz)."""
+    from xdem_b200 import coreg
+
+    g = parity.load_golden("nk_reference.npz")
+    tr = tuple(g["transform"])
+    for n_it in (1, 3, 6):
+        (e, n, v), n_used = coreg.nuth_kaab(g["ref"], g["tba"], inlier_mask=g["inlier"], transform=tr, tolerance=0.0,
+                                            max_iterations=n_it)
+        assert n_used == int(g["n_valid"])
+        assert np.allclose([e, n, v], g["offsets"][n_it - 1], rtol=1e-4, atol=2e-4), (n_it, (e, n, v))
+    nkc = coreg.NuthKaab(max_iterations=6, offset_threshold=0.0, subsample=1.0)
+    nkc.fit(g["ref"], g["tba"], inlier_mask=g["inlier"], transform=tr)
+    sx, sy, sz = nkc.to_translations()
+    # injected: tba = ref shifted by (+0.37, -0.61) px and +1.5 m  ->  shift_x = +0.37*5, shift_y = +0.61*5, z = -1.5
+    assert sx == pytest.approx(1.85, abs=0.01) and sy == pytest.approx(3.05, abs=0.01)
+    assert sz == pytest.approx(-1.5, abs=0.01)
+    assert np.allclose(nkc.to_matrix()[:3, 3], [sx, sy, sz])
+
+
+def test_nk_subsample_and_large() -> None:
+    """Larger pair on the device (2048^2) with the default-style subsample: recovers the injected shift."""
+    import torch
+
+    from oracle import synth
+    from xdem_b200 import coreg
+
+    ref, tba = synth.nk_pair((1024, 1280), shift_px=(-0.83, 0.42), dz=-2.0, noise=0.02)
+    nkc = coreg.NuthKaab(subsample=2e5)
+    nkc.fit(torch.from_numpy(ref).cuda(), torch.from_numpy(tba).cuda(), transform=(2.0, 0, 0, 0, -2.0, 0),
+            random_state=42)
+    sx, sy, sz = nkc.to_translations()
+    assert sx == pytest.approx(-0.83 * 2.0, abs=0.02) and sy == pytest.approx(-0.42 * 2.0, abs=0.02)
+    assert sz == pytest.approx(2.0, abs=0.02)
+    assert nkc.meta["outputs"]["random"]["subsample_final"] == 200000

@@ -1,0 +1,345 @@
+"""Nuth & Kaab (2011) coregistration hot path: drop-in for ``xdem.coreg.NuthKaab`` / ``xdem.coreg.affine.nuth_kaab``
+(affine.py:340-609, 2386-2541) for raster-raster inputs.
+
+What runs on the GPU (csrc/xb_nuthkaab.cu): the auxiliary slope-tangent / aspect rasters (np.gradient semantics,
+affine.py:435-438), the zero-slope mask (:578-579), the valid mask (base.py:653-661), every iteration's bilinear dh
+(:179-184), ``np.nanmedian(dh)`` (:504), ``dh/slope_tan`` (:381), its mean / std for the initial guess (:384) and the
+72-bin ``nanmedian`` over aspect (base.py:1014-1020 -> spatialstats.py:147-149) as exact medians by radix select.
+What stays on the host: the 72-point ``scipy.optimize.curve_fit`` of a*cos(b-x)+c (base.py:1038-1045), the iteration
+loop and stopping rule (affine.py:102-147).
+"""
+
+from __future__ import annotations
+
+import ctypes
+import logging
+from typing import Any, Callable, Iterable
+
+import numpy as np
+import scipy.optimize
+import torch
+
+from . import _arrays, _lib
+
+
+def _nuth_kaab_fit_func(xx: np.ndarray, *params: float) -> np.ndarray:
+    """y(x) = a * cos(b - x) + c  (affine.py:340-355)."""
+    return params[0] * np.cos(params[1] - xx) + params[2]
+
+
+def _transform_coeffs(transform: Any) -> tuple[float, float]:
+    """(a, e) pixel sizes (e < 0 for north-up) from an affine.Affine-like object or a 6/9-tuple (a,b,c,d,e,f)."""
+    if transform is None:
+        return 1.0, -1.0
+    if hasattr(transform, "a") and hasattr(transform, "e"):
+        return float(transform.a), float(transform.e)
+    t = tuple(transform)
+    return float(t[0]), float(t[4])
+
+
+def _ordered_to_float(key: np.ndarray) -> np.ndarray:
+    """inverse of the kernel's order-preserving float32 -> uint32 map."""
+    key = key.astype(np.uint32)
+    neg = (key & np.uint32(0x80000000)) == 0
+    bits = np.where(neg, ~key, key & np.uint32(0x7FFFFFFF)).astype(np.uint32)
+    return bits.view(np.float32)
+
+
+def _u32_tensor(a: np.ndarray, dev: torch.device) -> torch.Tensor:
+    """uint32 payload carried in an int32 tensor (bit pattern preserved)."""
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint32).view(np.int32).copy()).to(dev)
+
+
+class _NKState:
+    """Device-resident state of one Nuth-Kaab fit (one GPU / one row shard)."""
+
+    def __init__(self, ref: torch.Tensor, tba: torch.Tensor, inlier_mask: torch.Tensor | None, group: Any = None):
+        self.L = _lib.lib()
+        self.dev = ref.device
+        self.ref = ref.contiguous()
+        self.tba = tba.contiguous()
+        self.rows, self.cols = ref.shape
+        self.group = group
+        self.stream = ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        n = self.rows * self.cols
+        self.slope_tan = torch.empty((self.rows, self.cols), dtype=torch.float32, device=self.dev)
+        self.aspect = torch.empty_like(self.slope_tan)
+        with torch.cuda.device(self.dev):
+            _lib.check(self.L.xb_nk_aux(self.ref.data_ptr(), self.rows, self.cols, self.ref.stride(0), 1, 1, 0,
+                                        self.rows, self.slope_tan.data_ptr(), self.aspect.data_ptr(), self.cols,
+                                        self.stream))
+        # valid mask: inlier & finite(ref, tba, slope_tan, aspect)  (base.py:653-661)
+        valid = torch.isfinite(self.ref) & torch.isfinite(self.tba) & torch.isfinite(self.slope_tan) \
+            & torch.isfinite(self.aspect)
+        if inlier_mask is not None:
+            valid &= inlier_mask.to(self.dev).bool()
+        self.valid = valid
+        self.sub_mask = valid.to(torch.uint8).contiguous()
+        self.dh = torch.empty(n, dtype=torch.float32, device=self.dev)
+        self.n = n
+
+    # ------------------------------------------------------------------ device passes
+    def compute_dh(self, dx_px: float, dy_px: float) -> tuple[float, float, int]:
+        mm = _u32_tensor(np.array([0xFFFFFFFF, 0], dtype=np.uint32), self.dev)
+        cnt = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(self.L.xb_nk_dh(self.ref.data_ptr(), self.tba.data_ptr(), self.sub_mask.data_ptr(),
+                                       self.aspect.data_ptr(), self.rows, self.cols, self.ref.stride(0),
+                                       self.tba.stride(0), 0, self.rows, float(dx_px), float(dy_px),
+                                       self.dh.data_ptr(), mm.data_ptr(), cnt.data_ptr(), self.stream))
+        mmh = mm.cpu().numpy().view(np.uint32)
+        n_fin = int(cnt.item())
+        lo, hi = (float(v) for v in mmh.view(np.float32))
+        return lo, hi, n_fin
+
+    def _hist(self, mode: int, vshift: float, lo: float, hi: float, n_groups: int, prefix: np.ndarray,
+              prefix_mask: int, shift: int, n_digits: int, moments: torch.Tensor | None) -> np.ndarray:
+        hist = torch.zeros(n_groups * n_digits, dtype=torch.int64, device=self.dev)
+        pre = _u32_tensor(prefix, self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(self.L.xb_nk_hist(self.dh.data_ptr(), self.slope_tan.data_ptr(), self.aspect.data_ptr(), self.n,
+                                         mode, float(vshift), float(lo), float(hi), n_groups, pre.data_ptr(),
+                                         ctypes.c_uint32(prefix_mask), shift, n_digits, hist.data_ptr(),
+                                         moments.data_ptr() if moments is not None else None, self.stream))
+        self._allreduce(hist)
+        if moments is not None:
+            self._allreduce(moments)
+        return hist.cpu().numpy().reshape(n_groups, n_digits)
+
+    def _allreduce(self, t: torch.Tensor, op: Any = None) -> None:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(t, op=op or dist.ReduceOp.SUM, group=self.group)
+
+    def select_medians(self, mode: int, vshift: float, lo: float, hi: float, n_groups: int,
+                       want_moments: bool = False) -> tuple[np.ndarray, np.ndarray, np.ndarray | None]:
+        """Exact per-group medians (np.nanmedian semantics: mean of the two middle values for even counts) of the
+        float32 keys by 3-pass MSD radix select (11 + 11 + 10 bits).  Returns (median float64 [n_groups], count,
+        moments or None)."""
+        passes = [(21, 2048), (10, 2048), (0, 1024)]
+        prefix = np.zeros(n_groups, dtype=np.uint32)
+        prefix_mask = 0
+        moments_t = torch.zeros(3, dtype=torch.float64, device=self.dev) if want_moments else None
+        counts = None
+        k_lo = None  # 0-based rank of the lower median inside the still-selected bucket
+        below = np.zeros(n_groups, dtype=np.int64)  # number of keys < selected bucket so far
+        for ip, (shift, n_digits) in enumerate(passes):
+            hist = self._hist(mode, vshift, lo, hi, n_groups, prefix, prefix_mask, shift, n_digits,
+                              moments_t if ip == 0 else None)
+            if ip == 0:
+                counts = hist.sum(axis=1)
+                k_lo = (counts - 1) // 2
+            cum = np.cumsum(hist, axis=1)
+            digit = np.array([int(np.searchsorted(cum[g], k_lo[g] + 1 - below[g], side="left")) if counts[g] > 0 else 0
+                              for g in range(n_groups)], dtype=np.int64)
+            digit = np.minimum(digit, n_digits - 1)
+            below += np.where(digit > 0, cum[np.arange(n_groups), np.maximum(digit - 1, 0)], 0)
+            prefix = (prefix | (digit.astype(np.uint32) << np.uint32(shift))).astype(np.uint32)
+            prefix_mask |= (n_digits - 1) << shift
+            last_hist = hist[np.arange(n_groups), digit]
+        # prefix now holds the exact key of the lower median; `below` keys are smaller, `last_hist` are equal
+        lower = _ordered_to_float(prefix).astype(np.float64)
+        median = lower.copy()
+        even = (counts % 2 == 0) & (counts > 0)
+        need_next = even & (below + last_hist < (counts // 2 + 1))  # upper median is a strictly larger key
+        if need_next.any():
+            sel = _u32_tensor(prefix, self.dev)
+            nxt = _u32_tensor(np.full(n_groups, 0xFFFFFFFF, dtype=np.uint32), self.dev)
+            with torch.cuda.device(self.dev):
+                _lib.check(self.L.xb_nk_next(self.dh.data_ptr(), self.slope_tan.data_ptr(), self.aspect.data_ptr(),
+                                             self.n, mode, float(vshift), float(lo), float(hi), n_groups,
+                                             sel.data_ptr(), nxt.data_ptr(), self.stream))
+            import torch.distributed as dist
+
+            # unsigned order == signed order after flipping the top bit; all-reduce(min) over ranks on that
+            nxt64 = (nxt.to(torch.int64) & 0xFFFFFFFF)
+            self._allreduce(nxt64, op=dist.ReduceOp.MIN if dist.is_available() else None)
+            upper = _ordered_to_float(nxt64.cpu().numpy().astype(np.uint32)).astype(np.float64)
+            median = np.where(need_next, 0.5 * (lower + upper), median)
+        median = np.where(counts > 0, median, np.nan)
+        moments = moments_t.cpu().numpy() if moments_t is not None else None
+        return median, counts, moments
+
+
+def _nuth_kaab_bin_fit_gpu(state: _NKState, vshift: float, lo: float, hi: float, bin_sizes: int,
+                           fit_optimizer: Callable[..., Any]) -> tuple[float, float, float]:
+    """GPU restatement of `_nuth_kaab_bin_fit` + `_bin_or_and_fit_nd("bin_and_fit")` (affine.py:358-409,
+    base.py:1006-1045): y = dh/slope_tan; p0 = (3*nanstd(y)/sqrt(2), 0, nanmean(y)); per-aspect-bin nanmedian; fit."""
+    med, counts, mom = state.select_medians(1, vshift, lo, hi, int(bin_sizes), want_moments=True)
+    n, s1, s2 = mom
+    mean = s1 / n
+    std = float(np.sqrt(max(s2 / n - mean * mean, 0.0)))
+    p0 = (3 * std / (2**0.5), 0.0, float(mean))
+    # bin mid-points: pd.IntervalIndex.from_breaks(linspace(lo, hi, n+1)).mid  (spatialstats.py:153, base.py:1027)
+    edges = np.linspace(lo, hi, int(bin_sizes) + 1)
+    mids = 0.5 * (edges[:-1] + edges[1:])
+    ok = np.isfinite(med) & np.isfinite(mids)
+    if np.all(~ok):
+        raise ValueError("Only NaN values after binning, did you pass the right bin edges?")
+    results = fit_optimizer(f=_nuth_kaab_fit_func, xdata=mids[ok], ydata=med[ok], sigma=None, absolute_sigma=True,
+                            p0=p0)
+    a, b, c = results[0]
+    return a * np.sin(b), a * np.cos(b), c  # easting, northing, vertical (affine.py:405-407)
+
+
+def _nuth_kaab_iteration_step_gpu(coords_offsets: tuple[float, float, float], state: _NKState,
+                                  res: tuple[float, float], a_e: tuple[float, float], bin_sizes: int,
+                                  fit_optimizer: Callable[..., Any]) -> tuple[tuple[float, float, float], float]:
+    """affine.py:477-536."""
+    dx_px = coords_offsets[0] / a_e[0]
+    dy_px = coords_offsets[1] / a_e[1]
+    lo, hi, n_fin = state.compute_dh(dx_px, dy_px)
+    if n_fin == 0:
+        raise ValueError(
+            "The subsample contains no more valid values. This can happen is the horizontal shift to "
+            "correct is very large, or if the algorithm diverged. To ensure all possible points can "
+            "be used at any iteration step, use subsample=1."
+        )
+    med, _, _ = state.select_medians(0, 0.0, 0.0, 1.0, 1)
+    vshift = float(med[0])
+    easting, northing, _ = _nuth_kaab_bin_fit_gpu(state, vshift, lo, hi, bin_sizes, fit_optimizer)
+    new_offsets = (coords_offsets[0] + easting * res[0], coords_offsets[1] + northing * res[1], vshift)
+    return new_offsets, float(np.sqrt(easting**2 + northing**2))
+
+
+def nuth_kaab(ref_elev: Any, tba_elev: Any, inlier_mask: Any = None, transform: Any = None, crs: Any = None,
+              area_or_point: Any = None, tolerance: float = 0.001, max_iterations: int = 10,
+              params_fit_or_bin: dict[str, Any] | None = None, params_random: dict[str, Any] | None = None,
+              z_name: str = "z", weights: Any = None, **kwargs: Any) -> tuple[tuple[float, float, float], int]:
+    """Nuth and Kaab (2011) iterative coregistration on the GPU -- same contract as affine.py:539-609: returns the final
+    (easting, northing, vertical) offsets in georeferenced units and the number of points used."""
+    logging.info("Running Nuth and Kääb (2011) coregistration")
+    if crs is not None and hasattr(crs, "is_projected") and not crs.is_projected:
+        raise NotImplementedError(
+            f"NuthKaab coregistration only works with a projected CRS, current CRS is {crs}. Reproject "
+            f"your DEMs with DEM.reproject() in a local projected CRS such as UTM, that you can find "
+            f"using DEM.get_metric_crs()."
+        )
+    pf = dict(fit_or_bin="bin_and_fit", fit_optimizer=scipy.optimize.curve_fit, bin_sizes=72,
+              bin_statistic=np.nanmedian)
+    pf.update(params_fit_or_bin or {})
+    if pf["fit_or_bin"] not in ["fit", "bin_and_fit"]:
+        raise ValueError("Nuth and Kääb method only supports 'fit' or 'bin_and_fit'.")
+    if pf["fit_or_bin"] != "bin_and_fit" or pf["bin_statistic"] is not np.nanmedian or not isinstance(
+            pf["bin_sizes"], (int, np.integer)):
+        raise NotImplementedError("the B200 Nuth-Kaab path implements bin_and_fit with an integer number of aspect "
+                                  "bins and bin_statistic=np.nanmedian (the reference defaults)")
+    pr = dict(subsample=1.0, random_state=None)
+    pr.update(params_random or {})
+
+    ref_t, _ = _arrays.to_device(ref_elev)
+    tba_t, _ = _arrays.to_device(tba_elev)
+    if ref_t.dtype != torch.float32:
+        ref_t = ref_t.to(torch.float32)
+    if tba_t.dtype != torch.float32:
+        tba_t = tba_t.to(torch.float32)
+    if ref_t.shape != tba_t.shape or ref_t.dim() != 2:
+        raise ValueError("reference and to-be-aligned elevations must be 2-D rasters of the same shape")
+    mask_t = None
+    if inlier_mask is not None:
+        mask_t = inlier_mask if isinstance(inlier_mask, torch.Tensor) else torch.from_numpy(np.asarray(inlier_mask))
+    state = _NKState(ref_t, tba_t, mask_t)
+    n_valid = int(state.valid.sum().item())
+    if n_valid == 0:
+        raise ValueError(
+            "There is no valid points common to the input and auxiliary data (bias variables, or "
+            "derivatives required for this method, for example slope, aspect, etc)."
+        )
+    # subsample among the valid cells (base.py:576-621; geoutils.subsample_array's RNG stream is third-party)
+    sub = pr["subsample"]
+    if sub is not None and sub != 1.0:
+        want = int(sub) if sub > 1 else int(sub * n_valid)
+        if want < n_valid:
+            rng = np.random.default_rng(pr["random_state"])
+            idx_valid = torch.nonzero(state.valid.flatten()).flatten()
+            pick = torch.from_numpy(rng.choice(n_valid, size=want, replace=False)).to(state.dev)
+            m = torch.zeros(state.n, dtype=torch.uint8, device=state.dev)
+            m[idx_valid[pick]] = 1
+            state.sub_mask = m.view(state.rows, state.cols).contiguous()
+            n_valid = want
+    a_e = _transform_coeffs(transform)
+    res = (abs(a_e[0]), abs(a_e[1]))
+    offsets = (0.0, 0.0, 0.0)
+    for i in range(max_iterations):  # affine.py:102-147
+        offsets, stat = _nuth_kaab_iteration_step_gpu(offsets, state, res, a_e, int(pf["bin_sizes"]),
+                                                      pf["fit_optimizer"])
+        logging.info("      Iteration #%d - Offset: %s; Magnitude: %s", i + 1, offsets, stat)
+        if i > 1 and stat < tolerance:
+            logging.info("   Last offset was below the residual offset threshold of %s -> stopping", tolerance)
+            break
+    return offsets, n_valid
+
+
+class NuthKaab:
+    """Drop-in for ``xdem.coreg.NuthKaab`` (affine.py:2386-2541) for raster-raster fits.  Results are stored like the
+    reference in ``self.meta["outputs"]["affine"]`` (``shift_x``, ``shift_y``, ``shift_z``)."""
+
+    def __init__(self, max_iterations: int = 10, offset_threshold: float = 0.001, bin_before_fit: bool = True,
+                 fit_optimizer: Callable[..., Any] = scipy.optimize.curve_fit,
+                 bin_sizes: int | dict[str, int | Iterable[float]] = 72,
+                 bin_statistic: Callable[[np.ndarray], Any] = np.nanmedian, subsample: int | float = 5e5,
+                 vertical_shift: bool = True, initial_shift: Any = None) -> None:
+        if not callable(fit_optimizer):
+            raise TypeError("Argument `fit_optimizer` must be a function (callable), got {}.".format(type(fit_optimizer)))
+        if bin_before_fit and not (isinstance(bin_sizes, int) or isinstance(bin_sizes, dict)):
+            raise TypeError("Argument `bin_sizes` must be an integer, or a dictionary of integers or iterables, "
+                            "got {}.".format(type(bin_sizes)))
+        if bin_before_fit and not callable(bin_statistic):
+            raise TypeError("Argument `bin_statistic` must be a function (callable), got {}.".format(type(bin_statistic)))
+        if initial_shift is not None:
+            raise NotImplementedError("initial_shift is not supported by the B200 Nuth-Kaab path yet")
+        self.vertical_shift = vertical_shift
+        self._meta: dict[str, Any] = {
+            "inputs": {
+                "random": {"subsample": subsample, "random_state": None},
+                "fitorbin": {"fit_or_bin": "bin_and_fit" if bin_before_fit else "fit", "fit_optimizer": fit_optimizer,
+                             "bin_sizes": bin_sizes, "bin_statistic": bin_statistic},
+                "iterative": {"max_iterations": max_iterations, "tolerance": offset_threshold},
+            },
+            "outputs": {},
+        }
+        self._fit_called = False
+
+    @property
+    def meta(self) -> dict[str, Any]:
+        return self._meta
+
+    def fit(self, reference_elev: Any, to_be_aligned_elev: Any, inlier_mask: Any = None, bias_vars: Any = None,
+            weights: Any = None, subsample: float | int | None = None, transform: Any = None, crs: Any = None,
+            area_or_point: Any = None, z_name: str = "z", random_state: Any = None, **kwargs: Any) -> "NuthKaab":
+        """Estimate the x/y/z offsets (``Coreg.fit``, base.py:2250-2368, for two rasters on the same grid)."""
+        if _arrays.is_raster_like(reference_elev):
+            transform = transform or reference_elev.transform
+            crs = crs or reference_elev.crs
+            reference_elev = reference_elev.data
+        if _arrays.is_raster_like(to_be_aligned_elev):
+            to_be_aligned_elev = to_be_aligned_elev.data
+        pr = dict(self._meta["inputs"]["random"])
+        if subsample is not None:
+            pr["subsample"] = subsample
+        pr["random_state"] = random_state
+        (east, north, vert), n_used = nuth_kaab(
+            reference_elev, to_be_aligned_elev, inlier_mask=inlier_mask, transform=transform, crs=crs,
+            area_or_point=area_or_point, z_name=z_name, weights=weights, params_random=pr,
+            params_fit_or_bin=self._meta["inputs"]["fitorbin"],
+            max_iterations=self._meta["inputs"]["iterative"]["max_iterations"],
+            tolerance=self._meta["inputs"]["iterative"]["tolerance"])
+        # affine.py:2526-2530
+        self._meta["outputs"]["affine"] = {"shift_x": -east, "shift_y": -north,
+                                           "shift_z": vert * self.vertical_shift}
+        self._meta["outputs"]["random"] = {"subsample_final": n_used}
+        self._fit_called = True
+        return self
+
+    def to_matrix(self) -> np.ndarray:
+        """affine.py:2532-2541."""
+        matrix = np.diag(np.ones(4, dtype=float))
+        matrix[0, 3] += self._meta["outputs"]["affine"]["shift_x"]
+        matrix[1, 3] += self._meta["outputs"]["affine"]["shift_y"]
+        matrix[2, 3] += self._meta["outputs"]["affine"]["shift_z"]
+        return matrix
+
+    def to_translations(self) -> tuple[float, float, float]:
+        o = self._meta["outputs"]["affine"]
+        return o["shift_x"], o["shift_y"], o["shift_z"]
