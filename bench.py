@@ -20,7 +20,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -43,62 +42,59 @@ def _env_int(name: str, default: int) -> int:
 
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons with nvidia-smi during the timed region (B200_PROFILING.md)."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks / throttle reasons through NVML (nvidia_ml_py) in a thread during the timed region -- the same
+    fields as the `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` line of B200_PROFILING.md."""
 
     def __init__(self, gpu_index: int) -> None:
         self.gpu_index = gpu_index
-        self.rows: list[list[str]] = []
-        self.proc: subprocess.Popen | None = None
+        self.samples: list[tuple[float, int, int]] = []  # (time, sm_mhz, reasons bitmask)
+        self.max_mhz: float | None = None
+        self._stop = threading.Event()
         self.thread: threading.Thread | None = None
+        self.t0 = self.t1 = 0.0
 
     def start(self) -> None:
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
-                 str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
             return
 
-        def reader() -> None:
-            assert self.proc is not None and self.proc.stdout is not None
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+        def loop() -> None:
+            while not self._stop.is_set():
+                try:
+                    mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    try:
+                        rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    self.samples.append((time.perf_counter(), int(mhz), int(rs)))
+                except Exception:
+                    pass
+                time.sleep(0.002)
 
-        self.thread = threading.Thread(target=reader, daemon=True)
+        self.thread = threading.Thread(target=loop, daemon=True)
         self.thread.start()
 
+    def mark_begin(self) -> None:
+        self.t0 = time.perf_counter()
+
+    def mark_end(self) -> None:
+        self.t1 = time.perf_counter()
+
     def stop(self) -> dict:
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=5)
-            except subprocess.TimeoutExpired:
-                self.proc.kill()
+        self._stop.set()
         if self.thread is not None:
             self.thread.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            for name, v in zip(names, r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm_sorted = sorted(sm)
-        return {
-            "sm_mhz": sm_sorted[len(sm_sorted) // 2] if sm_sorted else None,
-            "sm_max_mhz": max(mx) if mx else None,
-            "reasons": sorted(reasons),
-            "samples": len(sm),
-        }
+        inside = [s for s in self.samples if self.t0 <= s[0] <= self.t1] or self.samples[-3:]
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = sorted({n for _, _, rs in inside for bit, n in names.items() if rs & bit})
+        mhz = sorted(m for _, m, _ in inside)
+        return {"sm_mhz": float(mhz[len(mhz) // 2]) if mhz else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(inside), "source": "NVML (nvidia_ml_py), 2 ms period, timed region only"}
 
 
 def measured_peak_gbs() -> tuple[float, str]:
@@ -238,22 +234,24 @@ def main() -> None:
         r_begin, r_end, view = shard.prepare(buf, rows)  # NCCL halo exchange (no-op at world=1)
         _engine.terrain_fused(view, RESOLUTION, row_begin=r_begin, row_end=r_end, out=out, **kwargs)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    sampler.mark_begin()
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     torch.cuda.synchronize()
+    sampler.mark_end()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - launches0
     if world > 1:
