@@ -48,7 +48,11 @@ def main() -> None:
     e, cnt, ssq = xs.pairwise_lag_binning(x, y, v, edges, 2.0)
     assert int(cnt.sum()) == N * (N - 1) // 2
     # single-rank reference: temporarily pretend world == 1 by using a 1-rank subgroup
-    sub = dist.new_group([rank])
+    sub = None
+    for r in range(world):  # new_group is collective: every rank creates every 1-rank group
+        grp = dist.new_group([r])
+        if r == rank:
+            sub = grp
     e1, cnt1, ssq1 = xs.pairwise_lag_binning(x, y, v, edges, 2.0, group=sub)
     assert np.array_equal(cnt, cnt1) and np.allclose(ssq, ssq1, rtol=1e-9)
     dist.barrier()

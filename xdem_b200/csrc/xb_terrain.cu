@@ -221,6 +221,127 @@ __device__ __forceinline__ Derivs<T> derivs_at(const T (&win)[2 * H + 1][4 + 2 *
 #undef WIN
 
 // ---------------------------------------------------------------------------------------------------------------
+// Curvature algebra (surfit.py:638-943).  out = {profile, tangential, planform, flowline, max, min} x 100.
+// N1 = zxx zx^2 + 2 zxy zx zy + zyy zy^2,  N2 = zxx zy^2 - 2 zxy zx zy + zyy zx^2,
+// N3 = zx zy (zxx - zyy) - zxy (zx^2 - zy^2),  K = zxx zyy - zxy^2,  Mn = (1+zy^2) zxx - 2 zxy zx zy + (1+zx^2) zyy.
+// Guards: g2 == 0 -> 0, except planform and geometric flowline which use g2 < 10e-15 (surfit.py:750, 780).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void curv_alg(T sx, T sy, T sxx, T syy, T sxy, const TerrainParams& p, T (&out)[6]);
+
+// float64 rasters: the reference's expressions verbatim in FP64
+template <>
+__device__ __forceinline__ void curv_alg<double>(double sx, double sy, double sxx, double syy, double sxy,
+                                                 const TerrainParams& p, double (&out)[6]) {
+    const double zx = sx * p.inv_d1, zy = sy * p.inv_d1, zxx = sxx * p.inv_d2, zyy = syy * p.inv_d2,
+                 zxy = sxy * p.inv_d3;
+    const double zx2 = zx * zx, zy2 = zy * zy, g2 = zx2 + zy2, zxzy = zx * zy, opg = 1.0 + g2;
+    const bool flat0 = (g2 == 0.0), flat_eps = (g2 < 10e-15);
+    const double n1 = zxx * zx2 + 2.0 * zxy * zxzy + zyy * zy2;
+    const double n2 = zxx * zy2 - 2.0 * zxy * zxzy + zyy * zx2;
+    const double n3 = zxzy * (zxx - zyy) - zxy * (zx2 - zy2);
+    out[0] = (flat0 ? 0.0 : -n1 / (p.curv_dir ? g2 : g2 * sqrt(opg * opg * opg))) * 100.0;
+    out[1] = (flat0 ? 0.0 : -n2 / (p.curv_dir ? g2 : g2 * sqrt(opg))) * 100.0;
+    out[2] = (flat_eps ? 0.0 : -n2 / sqrt(g2 * g2 * g2)) * 100.0;
+    out[3] = (p.curv_dir ? (flat0 ? 0.0 : n3 / sqrt(g2 * g2 * g2))
+                         : (flat_eps ? 0.0 : n3 / (sqrt(g2 * g2 * g2) * sqrt(opg)))) * 100.0;
+    double vmax, vmin;
+    if (p.curv_dir) {
+        const double half = (zxx + zyy) / 2.0, hd = (zxx - zyy) / 2.0, rad = sqrt(hd * hd + zxy * zxy);
+        vmax = -(half - rad);
+        vmin = -(half + rad);
+    } else {
+        const double mn = (1.0 + zy2) * zxx - 2.0 * zxy * zxzy + (1.0 + zx2) * zyy;
+        const double den = 2.0 * sqrt(opg * opg * opg);
+        const double mq = mn / den;
+        const double uns = sqrt(mq * mq - (zxx * zyy - zxy * zxy) / (opg * opg));
+        vmax = -mq + uns;
+        vmin = -mq - uns;
+    }
+    out[4] = (flat0 ? 0.0 : vmax) * 100.0;
+    out[5] = (flat0 ? 0.0 : vmin) * 100.0;
+}
+
+// float32 rasters: FP64 only where cancellation can occur (the numerators N1, N2, N3, K, Mn and the discriminant,
+// formed from the exact stencil sums); denominators, roots and reciprocals in fp32 (MUFU seeds + one Newton step);
+// max/min through the numerically stable root pair (product of the roots = 4 K (1+g2), resp. -K).
+template <>
+__device__ __forceinline__ void curv_alg<float>(float sx, float sy, float sxx, float syy, float sxy,
+                                                const TerrainParams& p, float (&out)[6]) {
+    const double zx = (double)sx * p.inv_d1, zy = (double)sy * p.inv_d1, zxx = (double)sxx * p.inv_d2,
+                 zyy = (double)syy * p.inv_d2, zxy = (double)sxy * p.inv_d3;
+    const double zx2 = zx * zx, zy2 = zy * zy, g2 = zx2 + zy2, zxzy = zx * zy;
+    const bool flat0 = (g2 == 0.0), flat_eps = (g2 < 10e-15);
+    const float g2f = (float)g2;
+    const float opgf = 1.0f + g2f;
+    float rg2 = xbm::rcp_approx(g2f);
+    rg2 = rg2 * fmaf(-g2f, rg2, 2.0f);  // Newton
+    float rs_opg = xbm::rsqrt_approx(opgf);
+    rs_opg = rs_opg * fmaf(-0.5f * opgf * rs_opg, rs_opg, 1.5f);
+    float rs_g2 = xbm::rsqrt_approx(g2f);
+    rs_g2 = rs_g2 * fmaf(-0.5f * g2f * rs_g2, rs_g2, 1.5f);
+    const double rg2d = (double)rg2;
+    const bool dir = p.curv_dir != 0;
+    const uint32_t m = p.surf_mask;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f;
+    if (m & (7u << 4)) {
+        if (m & (1u << 4)) {
+            const double n1 = zxx * zx2 + 2.0 * zxy * zxzy + zyy * zy2;
+            const float t = (float)(n1 * rg2d);
+            v0 = flat0 ? 0.f : -(dir ? t : t * (rs_opg * rs_opg * rs_opg));
+        }
+        if (m & (3u << 5)) {
+            const double n2 = zxx * zy2 - 2.0 * zxy * zxzy + zyy * zx2;
+            const float t = (float)(n2 * rg2d);
+            v1 = flat0 ? 0.f : -(dir ? t : t * rs_opg);
+            v2 = flat_eps ? 0.f : -(t * rs_g2);
+        }
+    }
+    if (m & (1u << 7)) {
+        const double n3 = zxzy * (zxx - zyy) - zxy * (zx2 - zy2);
+        const float t = (float)(n3 * rg2d) * rs_g2;
+        v3 = dir ? (flat0 ? 0.f : t) : (flat_eps ? 0.f : t * rs_opg);
+    }
+    if (m & (3u << 8)) {
+        const double K = zxx * zyy - zxy * zxy;
+        float big, prod, scale;
+        bool neg_disc = false;
+        if (dir) {
+            // roots -half +- rad of t^2 + 2 half t + K: product K... written for x = -half +- rad: x+ x- = half^2 - rad^2 = K
+            const double half = 0.5 * (zxx + zyy), hd = 0.5 * (zxx - zyy);
+            const float radf = xbm::sqrt_fast((float)(hd * hd + zxy * zxy));
+            big = (float)half;
+            prod = (float)K;
+            scale = 1.0f;
+            // x+ = -half + rad, x- = -half - rad
+            const float s = fabsf(big) + radf;
+            const float small = s > 0.f ? prod * xbm::rcp_approx(s) * fmaf(-s, xbm::rcp_approx(s), 2.0f) : 0.f;
+            v4 = big >= 0.f ? -small : s;  // half >= 0: x+ = -K/s ; else x+ = s
+            v5 = big >= 0.f ? -s : small;  // half >= 0: x- = -s   ; else x- = K/s
+        } else {
+            const double opg = 1.0 + g2;
+            const double mn = (1.0 + zy2) * zxx - 2.0 * zxy * zxzy + (1.0 + zx2) * zyy;
+            const double R = mn * mn - 4.0 * K * opg;  // discriminant: (Mn/den)^2 - K/opg^2 = R / den^2, den = 2 opg^1.5
+            neg_disc = R < 0.0;
+            const float sq = xbm::sqrt_fast((float)R);
+            big = (float)mn;
+            prod = (float)(4.0 * K * opg);
+            scale = 0.5f * (rs_opg * rs_opg * rs_opg);
+            // roots of x = (-Mn +- sqrt(R)) * scale, product of (-Mn + sq)(-Mn - sq) = Mn^2 - R = 4 K opg
+            const float s = fabsf(big) + sq;
+            const float rs = xbm::rcp_approx(s);
+            const float small = s > 0.f ? prod * rs * fmaf(-s, rs, 2.0f) : 0.f;
+            v4 = (big >= 0.f ? -small : s) * scale;
+            v5 = (big >= 0.f ? -s : small) * scale;
+        }
+        if (neg_disc) v4 = v5 = CUDART_NAN_F;  // the reference takes (negative)**0.5 = NaN there (surfit.py:851-867)
+        if (flat0) v4 = v5 = 0.f;
+    }
+    out[0] = v0 * 100.0f, out[1] = v1 * 100.0f, out[2] = v2 * 100.0f, out[3] = v3 * 100.0f, out[4] = v4 * 100.0f,
+    out[5] = v5 * 100.0f;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Kernel
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int HS, int HW, int RPW, bool USE_TMA, bool ALG>
@@ -366,60 +487,15 @@ terrain_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                         store4<T>(p.out[3], off, full, nvalid, cv);
                     }
                     if constexpr (ALG) if (need_curv_alg) {
-                        // Cancellation-prone algebra in FP64 (surfit.py:638-943), from the exact unscaled sums
+                        // Cancellation-prone algebra (surfit.py:638-943) from the exact unscaled sums: FP64 throughout
+                        // for float64 rasters; for float32 rasters FP64 numerators + fp32 denominators (curv_alg_mixed)
                         T o4[4], o5[4], o6[4], o7[4], o8[4], o9[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const double zx = (double)sx[k] * p.inv_d1, zy = (double)sy[k] * p.inv_d1;
-                            const double zxx = (double)sxx[k] * p.inv_d2, zyy = (double)syy[k] * p.inv_d2;
-                            const double zxy = (double)sxy[k] * p.inv_d3;
-                            const double zx2 = zx * zx, zy2 = zy * zy, g2 = zx2 + zy2, zxzy = zx * zy;
-                            const double opg = 1.0 + g2;
-                            const bool flat0 = (g2 == 0.0);
-                            const bool flat_eps = (g2 < 10e-15);
-                            const double n1 = zxx * zx2 + 2.0 * zxy * zxzy + zyy * zy2;
-                            const double n2 = zxx * zy2 - 2.0 * zxy * zxzy + zyy * zx2;
-                            const double carr = (double)car[k];
-                            if (p.surf_mask & (1u << 4)) {
-                                const double den = p.curv_dir ? g2 : g2 * sqrt(opg * opg * opg);
-                                o4[k] = (T)((flat0 ? 0.0 : -n1 / den) * 100.0 + carr);
-                            }
-                            if (p.surf_mask & (1u << 5)) {
-                                const double den = p.curv_dir ? g2 : g2 * sqrt(opg);
-                                o5[k] = (T)((flat0 ? 0.0 : -n2 / den) * 100.0 + carr);
-                            }
-                            if (p.surf_mask & (1u << 6)) {
-                                o6[k] = (T)((flat_eps ? 0.0 : -n2 / sqrt(g2 * g2 * g2)) * 100.0 + carr);
-                            }
-                            if (p.surf_mask & (1u << 7)) {
-                                const double n3 = zxzy * (zxx - zyy) - zxy * (zx2 - zy2);
-                                double v;
-                                if (p.curv_dir)
-                                    v = flat0 ? 0.0 : n3 / sqrt(g2 * g2 * g2);
-                                else
-                                    v = flat_eps ? 0.0 : n3 / (sqrt(g2 * g2 * g2) * sqrt(opg));
-                                o7[k] = (T)(v * 100.0 + carr);
-                            }
-                            if (p.surf_mask & (3u << 8)) {
-                                double vmax, vmin;
-                                if (p.curv_dir) {
-                                    const double half = (zxx + zyy) / 2.0;
-                                    const double hd = (zxx - zyy) / 2.0;
-                                    const double rad = sqrt(hd * hd + zxy * zxy);
-                                    vmax = -(half - rad);
-                                    vmin = -(half + rad);
-                                } else {
-                                    const double mn = (1.0 + zy2) * zxx - 2.0 * zxy * zxzy + (1.0 + zx2) * zyy;
-                                    const double den = 2.0 * sqrt(opg * opg * opg);
-                                    const double mean = -mn / den;
-                                    const double mq = mn / den;
-                                    const double uns = sqrt(mq * mq - (zxx * zyy - zxy * zxy) / (opg * opg));
-                                    vmax = mean + uns;
-                                    vmin = mean - uns;
-                                }
-                                o8[k] = (T)((flat0 ? 0.0 : vmax) * 100.0 + carr);
-                                o9[k] = (T)((flat0 ? 0.0 : vmin) * 100.0 + carr);
-                            }
+                            T r6[6];
+                            curv_alg<T>(sx[k], sy[k], sxx[k], syy[k], sxy[k], p, r6);
+                            o4[k] = r6[0] + car[k], o5[k] = r6[1] + car[k], o6[k] = r6[2] + car[k];
+                            o7[k] = r6[3] + car[k], o8[k] = r6[4] + car[k], o9[k] = r6[5] + car[k];
                         }
                         if (p.surf_mask & (1u << 4)) store4<T>(p.out[4], off, full, nvalid, o4);
                         if (p.surf_mask & (1u << 5)) store4<T>(p.out[5], off, full, nvalid, o5);
