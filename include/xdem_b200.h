@@ -90,6 +90,16 @@ int xb_terrain_fused_host(const void* dem_host, int dtype, int64_t rows, int64_t
                           int64_t rows_per_block);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Generic odd window (3..31) indexes and fractal roughness -- the reference's arbitrary `window_size`
+ * (window.py:926-1002) and `fractal_roughness` (window.py:317-379, terrain.py:620-633).
+ *  win_mask   bit 0 TPI, bit 1 TRI, bit 2 roughness, bit 4 fractal roughness (plane slots 0, 1, 2, 4 of a HOST array of
+ *             5 device pointers); same NaN rule and buffer / row-range conventions as xb_terrain_fused.
+ */
+int xb_windowed_generic(const void* dem_dev, int dtype, int64_t rows_buf, int64_t cols, int64_t ld, int64_t row_begin,
+                        int64_t row_end, int window_size, uint32_t win_mask, int tri_method_id,
+                        void* const* out_planes_host, int64_t out_ld, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Empirical variogram: all-pairs distance / squared-difference lag binning.
  * Replaces what skgstat.Variogram (third-party; scikit-gstat>=1.0.18, setup.cfg:56) computes for
  * xdem.spatialstats._get_pdist_empirical_variogram (spatialstats.py:1064-1101): for every sample pair i<j the lag class

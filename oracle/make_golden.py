@@ -68,6 +68,18 @@ def main() -> None:
                     outs = gta(dem, attrs, resolution=res, window_size=w, tri_method=tm, engine=engine)
                     for a, o in zip(attrs, outs):
                         store[f"win|{name}|{engine}|{w}|{tm}|{a}"] = o
+    # generic odd windows and fractal roughness (window.py:926-1002, 317-496)
+    for name in ("fractal", "small_int"):
+        dem = inputs[name]
+        for engine in ("scipy", "numba"):
+            for w in (7, 9):
+                for tm in ("Riley", "Wilson"):
+                    outs = gta(dem, WIN[:3], window_size=w, tri_method=tm, engine=engine)
+                    for a, o in zip(WIN[:3], outs):
+                        store[f"win|{name}|{engine}|{w}|{tm}|{a}"] = o
+            for wf in (13, 7):
+                store[f"frac|{name}|{engine}|{wf}"] = gta(dem, "fractal_roughness", window_size_fractal=wf, engine=engine)
+    store["frac64|fractal|scipy|13"] = gta(inputs["fractal"].astype(np.float64), "fractal_roughness", engine="scipy")
     # float64 input (out_dtype follows the input dtype, terrain.py:328-332)
     dem64 = inputs["fractal"].astype(np.float64) + 0.123456789
     store["in|fractal64"] = dem64

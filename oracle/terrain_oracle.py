@@ -207,12 +207,40 @@ def windowed_indexes(dem: np.ndarray, window_size: int, attrs: list[str], resolu
                 if window_size != 3:
                     raise ValueError("rugosity is defined on a 3x3 window")
                 v = _rugosity(z, cd.type(resolution), cd)
+            elif a == "fractal_roughness":  # window.py:402-446
+                v = _fractal_roughness(z, window_size)
             else:
                 raise ValueError(a)
             v = np.asarray(v)
-            v[~np.isfinite(np.sum(z * 0, axis=0))] = np.nan
+            if a == "fractal_roughness":
+                # only the top-left (w-1) x (w-1) cells of the window are read (window.py:356-358, 431)
+                used = z.reshape(window_size, window_size, *z.shape[1:])[: window_size - 1, : window_size - 1]
+                v[np.isnan(used).any(axis=(0, 1))] = np.nan
+            else:
+                v[~np.isfinite(np.sum(z * 0, axis=0))] = np.nan
             res[i] = v.astype(out_dtype)
     return res
+
+
+def _fractal_roughness(z: np.ndarray, w: int) -> np.ndarray:
+    """Taud & Parrot (2005) box counting, vectorized form window.py:402-446 (z is (w*w, H, W) row-major windows)."""
+    hw = w // 2
+    qs = [q for q in range(1, hw + 1) if hw % q == 0]
+    log_q = np.log(np.asarray(qs, dtype=np.int32))
+    mx = log_q.mean()
+    ss_xx = np.sum(log_q * log_q) - len(qs) * mx * mx
+    H, W = z.shape[1:]
+    zc = z[(w * w) // 2]
+    V = np.clip(z - zc, 0, w).reshape(w, w, H, W)
+    ns = []
+    for q in qs:
+        nq = (w - 1) // q
+        blocks = V[: nq * q, : nq * q].reshape(nq, q, nq, q, H, W)
+        ns.append(blocks.max(axis=(1, 3)).sum(axis=(0, 1)) / np.int32(q))
+    y = np.log(np.stack(ns, axis=-1))
+    my = y.mean(axis=-1)
+    ss_xy = np.sum(y * log_q, axis=-1) - len(qs) * my * mx
+    return -(ss_xy / ss_xx)
 
 
 def _rugosity(z: np.ndarray, L: float, cd: np.dtype) -> np.ndarray:
@@ -239,7 +267,7 @@ def get_terrain_attribute(dem: np.ndarray, attribute: list[str] | str, resolutio
                           hillshade_altitude: float = 45.0, hillshade_azimuth: float = 315.0,
                           hillshade_z_factor: float = 1.0, surface_fit: str = "Florinsky",
                           curv_method: str = "geometric", tri_method: str = "Riley", window_size: int = 3,
-                          out_dtype: np.dtype | None = None, coef_round: np.dtype | None = None,
+                          window_size_fractal: int = 13, out_dtype: np.dtype | None = None, coef_round: np.dtype | None = None,
                           window_compute_dtype: np.dtype | None = None) -> list[np.ndarray] | np.ndarray:
     """Restatement of ``_get_terrain_attribute`` (terrain.py:528-666) for ndarray input: integer -> float32
     (:560-561), rad2deg in the array dtype (:586-591), hillshade clip (:594-596), request order (:651-658)."""
@@ -252,6 +280,7 @@ def get_terrain_attribute(dem: np.ndarray, attribute: list[str] | str, resolutio
         dem = dem.astype(np.float32)
     surf = [a for a in attrs if a in SURFACE_ATTRS]
     win = [a for a in attrs if a in WINDOW_ATTRS]
+    frac = [a for a in attrs if a == "fractal_roughness"]
     res = {}
     if surf:
         s = surface_attributes(dem, resolution, surf, surface_fit, curv_method, hillshade_azimuth,
@@ -267,5 +296,8 @@ def get_terrain_attribute(dem: np.ndarray, attribute: list[str] | str, resolutio
         wv = windowed_indexes(dem, window_size, win, resolution, tri_method, out_dtype, window_compute_dtype)
         for i, a in enumerate(win):
             res[a] = wv[i]
+    if frac:
+        res["fractal_roughness"] = windowed_indexes(dem, window_size_fractal, frac, resolution, tri_method, out_dtype,
+                                                    window_compute_dtype)[0]
     out = [res[a] for a in attrs]
     return out[0] if single else out

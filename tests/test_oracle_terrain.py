@@ -159,3 +159,38 @@ def test_c_oracle_bit_exact_vs_numba_engine(name: str, fit: str) -> None:
             ww = co.windowed_indexes(dem, w, WIN[:3], tri_method=tm)
             for i, a in enumerate(WIN[:3]):
                 assert np.array_equal(ww[i], G[f"win|{name}|numba|{w}|{tm}|{a}"], equal_nan=True), (name, w, tm, a)
+
+
+@pytest.mark.parametrize("name", ["fractal", "small_int"])
+def test_oracle_generic_windows_and_fractal_vs_reference(name: str) -> None:
+    """window sizes 7 / 9 and fractal roughness (13, 7) against both reference engines."""
+    dem = G[f"in|{name}"]
+    for w in (7, 9):
+        for tm in ("Riley", "Wilson"):
+            outs = to.get_terrain_attribute(dem, WIN[:3], window_size=w, tri_method=tm)
+            for a, o in zip(WIN[:3], outs):
+                ref_s, ref_n = G[f"win|{name}|scipy|{w}|{tm}|{a}"], G[f"win|{name}|numba|{w}|{tm}|{a}"]
+                assert parity.nanmask_equal(o, ref_s) and parity.nanmask_equal(o, ref_n)
+                if a == "roughness":
+                    assert np.array_equal(o, ref_s, equal_nan=True)
+                elif a == "terrain_ruggedness_index":
+                    assert np.array_equal(o, ref_n, equal_nan=True)
+                elif name == "small_int":
+                    assert np.array_equal(o, ref_s, equal_nan=True)  # TPI on integer-valued DEM: exact
+    for wf in (13, 7):
+        o = to.get_terrain_attribute(dem, "fractal_roughness", window_size_fractal=wf)
+        for engine in ("scipy", "numba"):
+            ref = G[f"frac|{name}|{engine}|{wf}"]
+            assert parity.nanmask_equal(o, ref)
+            m = np.isfinite(ref)
+            assert np.allclose(o[m], ref[m], rtol=1e-5, atol=2e-6)
+
+
+def test_fractal_roughness_known_answers() -> None:
+    """test_window.py:70-89: line -> 1, plane -> 2, cube -> 3."""
+    for setter, expect in ((lambda d: d.__setitem__((1, 1), 6.5), 1.0), (lambda d: d.__setitem__((slice(None), 1), 13), 2.0),
+                           (lambda d: d.__setitem__((slice(None), slice(None, 6)), 13), 3.0)):
+        dem = np.zeros((13, 13), dtype="float64")
+        setter(dem)
+        fr = to.get_terrain_attribute(dem, "fractal_roughness")
+        assert np.round(fr[6, 6], 3) == np.float32(expect)

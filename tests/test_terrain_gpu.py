@@ -333,3 +333,63 @@ def test_math_accuracy_sweep(xb) -> None:
             else:
                 rel = d / np.maximum(np.abs(r[m]), 1e-300)
             assert rel.max() < 6e-7, (fit, a, rel.max())
+
+
+@pytest.mark.parametrize("name", ["fractal", "small_int"])
+def test_generic_windows_and_fractal_vs_reference(xb, G, name: str) -> None:
+    """window sizes 7 / 9 (generic odd-window kernel) and fractal roughness against the reference fixtures."""
+    dem = G[f"in|{name}"]
+    for w in (7, 9):
+        for tm in ("Riley", "Wilson"):
+            outs = xb.terrain.get_terrain_attribute(dem, WIN[:3], window_size=w, tri_method=tm)
+            for a, o in zip(WIN[:3], outs):
+                ref_s, ref_n = G[f"win|{name}|scipy|{w}|{tm}|{a}"], G[f"win|{name}|numba|{w}|{tm}|{a}"]
+                assert o.dtype == np.float32 and parity.nanmask_equal(o, ref_s)
+                if a == "roughness":
+                    assert np.array_equal(o, ref_s, equal_nan=True)
+                elif a == "terrain_ruggedness_index":
+                    assert np.array_equal(o, ref_n, equal_nan=True)
+                elif name == "small_int":
+                    assert np.array_equal(o, ref_s, equal_nan=True)
+                else:
+                    assert np.nanmax(np.abs(o - ref_s)) <= 4 * np.spacing(np.float32(np.nanmax(np.abs(dem)) * w * w))
+    for wf in (13, 7):
+        o = xb.terrain.fractal_roughness(dem, window_size_fractal=wf) if wf == 13 else \
+            xb.terrain.get_terrain_attribute(dem, "fractal_roughness", window_size_fractal=wf)
+        for engine in ("scipy", "numba"):
+            ref = G[f"frac|{name}|{engine}|{wf}"]
+            assert parity.nanmask_equal(o, ref), (wf, engine)
+            m = np.isfinite(ref)
+            assert np.allclose(o[m], ref[m], rtol=1e-5, atol=2e-6)
+    o64 = xb.terrain.fractal_roughness(G["in|fractal"].astype(np.float64))
+    ref64 = G["frac64|fractal|scipy|13"]
+    assert o64.dtype == np.float64 and parity.nanmask_equal(o64, ref64)
+    assert np.allclose(o64[np.isfinite(ref64)], ref64[np.isfinite(ref64)], rtol=1e-12)
+
+
+def test_fractal_roughness_known_answers(xb) -> None:
+    """test_window.py:70-89."""
+    for setter, expect in ((lambda d: d.__setitem__((1, 1), 6.5), 1.0), (lambda d: d.__setitem__((slice(None), 1), 13), 2.0),
+                           (lambda d: d.__setitem__((slice(None), slice(None, 6)), 13), 3.0)):
+        dem = np.zeros((13, 13), dtype="float64")
+        setter(dem)
+        assert np.round(xb.terrain.fractal_roughness(dem)[6, 6], 3) == np.float32(expect)
+
+
+def test_mixed_request_all_paths(xb, G) -> None:
+    """One call mixing the fused kernel, the 3x3 rugosity special case, a generic window and fractal roughness keeps the
+    request order and equals the single-attribute calls (terrain.py:651-658)."""
+    dem = G["in|fractal"]
+    req = ["fractal_roughness", "slope", "rugosity", "roughness", "topographic_position_index", "max_curvature"]
+    outs = xb.terrain.get_terrain_attribute(dem, req, resolution=5.0, window_size=7)
+    assert np.array_equal(outs[0], xb.terrain.fractal_roughness(dem), equal_nan=True)
+    assert np.array_equal(outs[1], xb.terrain.slope(dem, resolution=5.0), equal_nan=True)
+    assert np.array_equal(outs[2], xb.terrain.rugosity(dem, resolution=5.0), equal_nan=True)
+    assert np.array_equal(outs[3], xb.terrain.roughness(dem, window_size=7), equal_nan=True)
+    assert np.array_equal(outs[4], xb.terrain.topographic_position_index(dem, window_size=7), equal_nan=True)
+    assert np.array_equal(outs[5], xb.terrain.max_curvature(dem, resolution=5.0), equal_nan=True)
+    from xdem_b200.window import _get_windowed_indexes
+
+    seam = _get_windowed_indexes(dem, 7, ["roughness", "fractal_roughness"], 5.0)
+    assert seam.shape == (2,) + dem.shape
+    assert np.array_equal(seam[0], outs[3], equal_nan=True)

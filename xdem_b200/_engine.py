@@ -154,3 +154,36 @@ def terrain_fused_host(
             int(rows_per_block))
     _lib.check(rc)
     return out
+
+
+GENERIC_SLOTS = {"topographic_position_index": 0, "terrain_ruggedness_index": 1, "roughness": 2, "fractal_roughness": 4}
+
+
+def windowed_generic(dem: torch.Tensor, window_size: int, windowed_indexes: Sequence[str], tri_method: str = "Riley",
+                     row_begin: int = 0, row_end: int | None = None) -> torch.Tensor:
+    """Any odd window (3..31): TPI / TRI / roughness / fractal roughness (xb_windowed_generic).  Returns
+    (n_attr, rows, cols) in the order of ``windowed_indexes``."""
+    if not dem.is_cuda or dem.dim() != 2:
+        raise ValueError("dem must be a 2-D CUDA tensor")
+    if dem.stride(1) != 1:
+        dem = dem.contiguous()
+    L = _lib.lib()
+    rows_buf, cols = dem.shape
+    if row_end is None:
+        row_end = rows_buf
+    out = torch.empty((len(windowed_indexes), row_end - row_begin, cols), dtype=dem.dtype, device=dem.device)
+    planes = (ctypes.c_void_p * 5)()
+    mask = 0
+    for i, a in enumerate(windowed_indexes):
+        slot = GENERIC_SLOTS[a]
+        if mask >> slot & 1:
+            raise ValueError(f"duplicate attribute {a}")
+        mask |= 1 << slot
+        planes[slot] = out[i].data_ptr()
+    stream = torch.cuda.current_stream(dem.device).cuda_stream
+    with torch.cuda.device(dem.device):
+        rc = L.xb_windowed_generic(dem.data_ptr(), _dtype_code(dem), rows_buf, cols, dem.stride(0), row_begin, row_end,
+                                   int(window_size), mask, 0 if tri_method.lower() == "riley" else 1, planes, cols,
+                                   ctypes.c_void_p(stream))
+    _lib.check(rc)
+    return out

@@ -183,41 +183,61 @@ def _get_terrain_attribute(
     texture_alpha: float = 0.8,
     out_dtype: Any = None,
 ) -> Any:
-    """terrain.py:528-666 with the surface-fit and windowed groups fused into one kernel launch."""
-    surf = [a for a in attribute if a in list_requiring_surface_fit]
-    win = [a for a in attribute if a in list_requiring_windowed_index]
-    other = [a for a in attribute if a in list_requiring_windowed_fractal_index + list_requiring_frequency_domain]
+    """terrain.py:528-666 with the surface-fit and windowed groups fused into one kernel launch.  Window sizes other
+    than 3/5 and fractal roughness (terrain.py:620-633) go through the generic odd-window kernel."""
+    surf = list(dict.fromkeys(a for a in attribute if a in list_requiring_surface_fit))
+    win = list(dict.fromkeys(a for a in attribute if a in list_requiring_windowed_index))
+    frac = [a for a in attribute if a in list_requiring_windowed_fractal_index]
+    other = [a for a in attribute if a in list_requiring_frequency_domain]
     if other:
         raise NotImplementedError(
-            f"{other} are not on the B200 hot path (SURVEY.md section 8f: fractal roughness rank 1, texture shading "
-            "rank 4); use the reference CPU implementation for them."
+            f"{other} is not on the B200 hot path (SURVEY.md section 8f rank 4: global FFT); use the reference CPU "
+            "implementation for it."
         )
-    if win and window_size not in (3, 5):
-        raise NotImplementedError(f"the B200 engine supports window_size 3 or 5 (got {window_size})")
-    if len(set(attribute)) != len(attribute):
-        # the reference recomputes duplicates; we compute once and fan out below
-        pass
+    for ws in ([window_size] if win else []) + ([window_size_fractal] if frac else []):
+        if ws < 3 or ws > 31 or ws % 2 == 0:
+            raise NotImplementedError(f"the B200 engine supports odd window sizes between 3 and 31 (got {ws})")
+
+    # which launches are needed: the fused kernel takes 3x3 / 5x5 windows; rugosity is always 3x3 in the reference's
+    # default engine (window.py:909-914 ignores window_size)
+    fused_win = [a for a in win if (window_size in (3, 5) and not (a == "rugosity" and window_size != 3))]
+    rug_separate = "rugosity" in win and "rugosity" not in fused_win
+    generic_win = [a for a in win if a not in fused_win and a != "rugosity"]
+    needs_device = bool(generic_win or frac or rug_separate)
 
     is_raster = _arrays.is_raster_like(dem)
-    uniq_surf = list(dict.fromkeys(surf))
-    uniq_win = list(dict.fromkeys(win))
-    index = {a: i for i, a in enumerate(uniq_surf + uniq_win)}
-    kwargs = dict(surface_attributes=uniq_surf, windowed_indexes=uniq_win, surface_fit=surface_fit,
-                  curv_method=curv_method, tri_method=tri_method, window_size=window_size, degrees=degrees,
+    kwargs = dict(surface_fit=surface_fit, curv_method=curv_method, tri_method=tri_method, degrees=degrees,
                   clip_hillshade=True, hillshade_azimuth=hillshade_azimuth, hillshade_altitude=hillshade_altitude,
                   hillshade_z_factor=hillshade_z_factor)
-    if isinstance(dem, torch.Tensor) and dem.is_cuda:
-        # device-resident raster: one launch, CUDA tensors out
-        t, kind = _arrays.to_device(dem)
-        planes = _engine.terrain_fused(t, float(resolution), **kwargs)
-        outs = [_arrays.from_device(planes[index[a]], kind, out_dtype) for a in attribute]
+    on_device = isinstance(dem, torch.Tensor) and dem.is_cuda
+    as_tensor = isinstance(dem, torch.Tensor)
+    planes: dict[str, Any] = {}
+    if on_device or needs_device:
+        t, _ = _arrays.to_device(dem)
+        if surf or fused_win:
+            out = _engine.terrain_fused(t, float(resolution), surface_attributes=surf, windowed_indexes=fused_win,
+                                        window_size=window_size if fused_win else 3, **kwargs)
+            planes.update({a: out[i] for i, a in enumerate(surf + fused_win)})
+        if rug_separate:
+            planes["rugosity"] = _engine.terrain_fused(t, float(resolution), windowed_indexes=["rugosity"],
+                                                       window_size=3)[0]
+        if generic_win:
+            out = _engine.windowed_generic(t, window_size, generic_win, tri_method=tri_method)
+            planes.update({a: out[i] for i, a in enumerate(generic_win)})
+        if frac:
+            planes["fractal_roughness"] = _engine.windowed_generic(t, window_size_fractal, ["fractal_roughness"])[0]
+        kind = "torch" if on_device else "numpy"
+        outs = [_arrays.from_device(planes[a], kind, out_dtype) for a in attribute]
+        if as_tensor and not on_device:
+            outs = [torch.from_numpy(o) for o in outs]
     else:
         # host raster (ndarray / masked array / Raster / CPU tensor): streamed through the GPU in row blocks
-        as_tensor = isinstance(dem, torch.Tensor)
         arr = dem.numpy() if as_tensor else _arrays.to_host_nan_array(dem)
         if arr.dtype not in (np.float32, np.float64):
             arr = arr.astype(np.float32)
-        planes_h = _engine.terrain_fused_host(arr, float(resolution), **kwargs)
+        planes_h = _engine.terrain_fused_host(arr, float(resolution), surface_attributes=surf,
+                                              windowed_indexes=fused_win, window_size=window_size, **kwargs)
+        index = {a: i for i, a in enumerate(surf + fused_win)}
         outs = []
         for a in attribute:
             o = planes_h[index[a]]
@@ -350,7 +370,7 @@ def rugosity(dem: Any, resolution: float | tuple[float, float] | None = None, mp
 
 
 def fractal_roughness(dem: Any, window_size_fractal: int = 13, mp_config: Any = None, engine: str = "b200") -> Any:
-    """terrain.py:1722-1763 -- not on the B200 hot path yet: raises NotImplementedError."""
+    """terrain.py:1722-1763 (box-counting fractal dimension on a `window_size_fractal` window, default 13)."""
     return get_terrain_attribute(dem=dem, attribute="fractal_roughness", window_size_fractal=window_size_fractal,
                                  mp_config=mp_config, engine=engine)
 
