@@ -55,6 +55,9 @@ const char* xb_last_error(void);
 int xb_version(void);
 /* Number of kernels this library launched since load (all entry points); bench.py reports it as gpu_launches. */
 uint64_t xb_launch_count(void);
+/* Tuning / test knobs.  "florinsky_generic" = 1 routes Florinsky requests through the generic fused kernel instead of
+ * the row-feature-reuse kernel (both are parity-tested; used for A/B checks). */
+int xb_set_option(const char* name, int value);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Terrain stencil engine.

@@ -393,3 +393,44 @@ def test_mixed_request_all_paths(xb, G) -> None:
     seam = _get_windowed_indexes(dem, 7, ["roughness", "fractal_roughness"], 5.0)
     assert seam.shape == (2,) + dem.shape
     assert np.array_equal(seam[0], outs[3], equal_nan=True)
+
+
+@pytest.mark.parametrize("shape", [(64, 128), (61, 132), (300, 1028), (7, 8), (1200, 516)])
+def test_florinsky_sliding_kernel_vs_generic_and_oracle(xb, shape) -> None:
+    """The row-feature-reuse Florinsky kernel (xb_terrain_fl.cu, taken for 16-byte aligned float32 rasters when a
+    second-derivative attribute is requested) against the generic fused kernel and the float64 oracle; integer-valued
+    DEMs must agree bit-for-bit (every stencil sum is exact in both)."""
+    import torch
+
+    from oracle import synth
+    from oracle import terrain_oracle as to
+    from xdem_b200 import _engine, _lib
+
+    attrs = ["slope", "aspect", "hillshade", "curvature", "profile_curvature", "planform_curvature", "max_curvature",
+             "min_curvature"]
+    dem = synth.inject_nans(synth.fractal_dem(shape, seed=21), frac=0.003, hole=3) if shape[0] > 10 else \
+        synth.fractal_dem(shape, seed=21)
+    idem = synth.integer_dem(shape, seed=22, high=500)
+    for d, exact in ((dem, False), (idem, True)):
+        t = torch.from_numpy(d).cuda()
+        kw = dict(surface_fit="Florinsky", degrees=True, clip_hillshade=True)
+        _lib.set_option("florinsky_generic", 0)
+        n0 = _lib.launch_count()
+        a = _engine.terrain_fused(t, 5.0, attrs, **kw).cpu().numpy()
+        _lib.set_option("florinsky_generic", 1)
+        try:
+            b = _engine.terrain_fused(t, 5.0, attrs, **kw).cpu().numpy()
+        finally:
+            _lib.set_option("florinsky_generic", 0)
+        assert _lib.launch_count() == n0 + 2
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        keep = to.get_terrain_attribute(d.astype(np.float64), "slope", resolution=5.0) > 1e-3
+        for i, name in enumerate(attrs):
+            if exact and name in ("slope", "hillshade", "curvature"):
+                assert np.array_equal(a[i], b[i], equal_nan=True), name
+            parity.assert_attr_close(a[i], b[i], name, where=keep, atol_scale=20.0 if exact else 1.0,
+                                     msg=f"sliding vs generic {shape}")
+        if not exact:
+            ref = to.get_terrain_attribute(d, attrs, resolution=5.0)
+            for i, name in enumerate(attrs):
+                parity.assert_attr_close(a[i], ref[i], name, where=keep, msg=f"sliding vs oracle {shape}")

@@ -40,6 +40,8 @@ def lib() -> ctypes.CDLL:
         L.xb_terrain_fused_host.argtypes = [c_void_p, c_int, c_int64, c_int64, c_double, c_int, c_int, c_uint32,
                                             c_uint32, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
                                             ctypes.POINTER(c_void_p), c_int64]
+    L.xb_set_option.restype = c_int
+    L.xb_set_option.argtypes = [c_char_p, c_int]
     L.xb_windowed_generic.restype = c_int
     L.xb_windowed_generic.argtypes = [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_uint32,
                                       c_int, ctypes.POINTER(c_void_p), c_int64, c_void_p]
@@ -72,6 +74,10 @@ def check(rc: int) -> None:
         raise XdemB200Error(f"libxdem_b200 error {rc}: {msg}")
 
 
+def set_option(name: str, value: int) -> None:
+    check(lib().xb_set_option(name.encode(), int(value)))
+
+
 def launch_count() -> int:
     return int(lib().xb_launch_count())
 
@@ -79,6 +85,6 @@ def launch_count() -> int:
 #: every symbol declared in include/xdem_b200.h (checked by tests/test_abi.py)
 EXPORTED = ["xb_last_error", "xb_version", "xb_launch_count", "xb_terrain_fused", "xb_terrain_fused_host",
             "xb_variogram_group_size", "xb_variogram_chunk", "xb_variogram_pairs", "xb_variogram_maxd2", "xb_nk_aux",
-            "xb_nk_dh", "xb_nk_hist", "xb_nk_next", "xb_windowed_generic"]
+            "xb_nk_dh", "xb_nk_hist", "xb_nk_next", "xb_windowed_generic", "xb_set_option"]
 
 __all__ = ["lib", "check", "launch_count", "XdemB200Error", "LIB_PATH", "EXPORTED", "c_int32"]

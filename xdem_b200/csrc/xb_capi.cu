@@ -21,6 +21,9 @@ void xb_set_error(const char* fmt, ...) {
 
 void xb_count_launch(int n) { g_launches.fetch_add((unsigned long long)n); }
 
+static std::atomic<int> g_opt_fl_generic{0};
+bool xb_option_florinsky_generic() { return g_opt_fl_generic.load() != 0; }
+
 xb_cuTensorMapEncodeTiled_t xb_get_tensormap_encoder() {
     static xb_cuTensorMapEncodeTiled_t fn = nullptr;
     static bool tried = false;
@@ -148,6 +151,15 @@ extern "C" {
 const char* xb_last_error(void) { return g_err; }
 int xb_version(void) { return 100; }
 uint64_t xb_launch_count(void) { return g_launches.load(); }
+
+int xb_set_option(const char* name, int value) {
+    if (name && strcmp(name, "florinsky_generic") == 0) {
+        g_opt_fl_generic.store(value);
+        return XB_OK;
+    }
+    xb_set_error("unknown option '%s'", name ? name : "(null)");
+    return XB_ERR_INVALID;
+}
 
 int xb_terrain_fused(const void* dem_dev, int dtype, int64_t rows_buf, int64_t cols, int64_t ld, int64_t row_begin,
                      int64_t row_end, double resolution, int fit_id, int curv_method_id, uint32_t surf_mask,

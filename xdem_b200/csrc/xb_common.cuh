@@ -86,3 +86,4 @@ typedef CUresult (*xb_cuTensorMapEncodeTiled_t)(CUtensorMap*, CUtensorMapDataTyp
                                                 CUtensorMapFloatOOBfill);
 xb_cuTensorMapEncodeTiled_t xb_get_tensormap_encoder();
 int xb_num_sms(int* out);
+bool xb_option_florinsky_generic();

@@ -31,6 +31,8 @@ struct TerrainParams {
 };
 
 int launch(const TerrainParams& p, int dtype, int hs, int hw, cudaStream_t stream);
+// float32 Florinsky surface attributes with row-feature reuse (xb_terrain_fl.cu); needs a TMA-eligible raster
+int launch_florinsky_sliding(const TerrainParams& p, cudaStream_t stream);
 int tile_rows(int halo);
 
 }  // namespace xbt

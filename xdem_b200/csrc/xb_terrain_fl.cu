@@ -1,0 +1,278 @@
+// xdem_b200 -- Florinsky (5x5) surface-fit kernel with row-feature reuse ("sliding window"), float32, sm_100a.
+//
+// The generic fused kernel (xb_terrain.cu) rebuilds every pixel's 5x5 stencil from scratch: ~93 FP ops per pixel for the
+// four derivatives of slope+aspect+hillshade+curvature, which makes it FMA-pipe bound (ncu: 206 thread-instructions per
+// pixel, 66 % FMA-pipe utilisation).  Here each lane owns a 2-pixel-wide column strip and marches down it; for every
+// input row it computes, ONCE, the per-pixel row features
+//     p = (w[-2]-c) + (w[2]-c),  q = (w[-1]-c) + (w[1]-c)   (second differences about the row centre c = w[0]),
+//     D = w[2] - w[-2],          E = w[-1] - w[1]           (first differences),
+// keeps the features of the last five rows in registers (a statically indexed ring, the row loop is unrolled by 5) and
+// combines them vertically with the Florinsky weights (surfit.py:204-252; effective weights SURVEY.md A.1):
+//     z_x  ~ sum_r a_r D_r + b_r E_r                     a = [31,-5,-17,-5,31], b = [44,62,68,62,44]
+//     z_y  ~ 31 (p-2 - p2) - 5 (q-2 - q2) + 44 (p1 - p-1) + 62 (q1 - q-1) + 35 (c-2 - c2) + 280 (c1 - c-1)
+//     z_xx ~ sum_r (2 p_r - q_r)
+//     z_yy ~ [2 (P-2 + P2) - (P-1 + P1) - 2 P0] with P = p + q,  + 5 [2((c-2-c0)+(c2-c0)) - ((c-1-c0)+(c1-c0))]
+//     z_xy ~ -(M11 + 2 (M12 + M21) + 4 M22),  M from differences of D / E between rows +-1, +-2
+// Every term is a difference-first integer combination, exact in fp32 like the generic kernel.  ~54 FP ops
+// per pixel for the same four derivatives.  Same tiles, TMA staging, NaN rule, attribute math and outputs as the generic
+// kernel; results are identical up to the association order of exact sums (tested bit-for-bit on integer DEMs and to
+// <= 1e-6 relative against the generic kernel / reference fixtures).
+#include <stdlib.h>
+
+#include "xb_terrain_dev.cuh"
+
+namespace xbt {
+
+constexpr int FL_RPW = 15;                 // output rows per warp (multiple of 5: ring period)
+constexpr int FL_WY = 4;                   // warps along y
+constexpr int FL_TH = FL_WY * FL_RPW;      // 60 output rows per tile
+constexpr int FL_BOXH = FL_TH + 4;         // 64 staged rows
+
+struct RowFeat {
+    float p[2], q[2], D[2], E[2], c[2];
+};
+
+__device__ __forceinline__ void make_features(const float* row, RowFeat& f) {
+    // row points at shared-memory column (x0 - 2); 6 values cover both pixels' 5-wide windows
+    const float2 a = *reinterpret_cast<const float2*>(row);
+    const float2 b = *reinterpret_cast<const float2*>(row + 2);
+    const float2 d = *reinterpret_cast<const float2*>(row + 4);
+    const float w[6] = {a.x, a.y, b.x, b.y, d.x, d.y};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float c = w[k + 2];
+        f.c[k] = c;
+        f.p[k] = (w[k] - c) + (w[k + 4] - c);
+        f.q[k] = (w[k + 1] - c) + (w[k + 3] - c);
+        f.D[k] = w[k + 4] - w[k];
+        f.E[k] = w[k + 1] - w[k + 3];
+    }
+}
+
+__device__ __forceinline__ void store2(void* plane, long long off, bool full, int nvalid, float v0, float v1) {
+    float* p = reinterpret_cast<float*>(plane) + off;
+    if (full) {
+        __stcs(reinterpret_cast<float2*>(p), make_float2(v0, v1));
+    } else {
+        if (nvalid > 0) __stcs(p, v0);
+        if (nvalid > 1) __stcs(p + 1, v1);
+    }
+}
+
+// rows r = -2..2 of the current output row are ring slots S0..S4
+template <bool ALG>
+__device__ __forceinline__ void emit_row(const RowFeat& r0, const RowFeat& r1, const RowFeat& r2, const RowFeat& r3,
+                                         const RowFeat& r4, const TerrainParams& p, long long off, bool full, int nvalid,
+                                         bool need2, bool need_sah) {
+    float sx[2], sy[2], sxx[2], syy[2], sxy[2], car[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        // z_x (fl_p, divider 420 res)
+        sx[k] = 31.0f * (r0.D[k] + r4.D[k]) - 5.0f * (r1.D[k] + r3.D[k]) - 17.0f * r2.D[k] +
+                44.0f * (r0.E[k] + r4.E[k]) + 62.0f * (r1.E[k] + r3.E[k]) + 68.0f * r2.E[k];
+        // z_y (fl_q): row sums about the row centres + the centre-column differences
+        sy[k] = (31.0f * (r0.p[k] - r4.p[k]) - 5.0f * (r0.q[k] - r4.q[k])) +
+                (44.0f * (r3.p[k] - r1.p[k]) + 62.0f * (r3.q[k] - r1.q[k])) +
+                (35.0f * (r0.c[k] - r4.c[k]) + 280.0f * (r3.c[k] - r1.c[k]));
+        const float pp2 = r0.p[k] + r4.p[k], pp1 = r1.p[k] + r3.p[k];
+        const float qq2 = r0.q[k] + r4.q[k], qq1 = r1.q[k] + r3.q[k];
+        // z_xx (fl_r, 35 res^2) = sum_r (2 p_r - q_r): propagates NaN / inf from every cell of the 5x5 window
+        const float sp = (pp2 + pp1) + r2.p[k], sq = (qq2 + qq1) + r2.q[k];
+        sxx[k] = 2.0f * sp - sq;
+        car[k] = sxx[k] * 0.0f;
+        sxy[k] = 0.0f;
+        syy[k] = 0.0f;
+        if (need2) {
+            // z_yy (fl_t, 35 res^2)
+            const float tp = 2.0f * (pp2 - r2.p[k]) - pp1;
+            const float tq = 2.0f * (qq2 - r2.q[k]) - qq1;
+            const float a2 = (r0.c[k] - r2.c[k]) + (r4.c[k] - r2.c[k]);
+            const float a1 = (r1.c[k] - r2.c[k]) + (r3.c[k] - r2.c[k]);
+            syy[k] = (tp + tq) + 5.0f * (2.0f * a2 - a1);
+            if (ALG) {
+                // z_xy (fl_s, 100 res^2): mixed second differences
+                const float m11 = r1.E[k] - r3.E[k], m12 = r3.D[k] - r1.D[k];
+                const float m21 = r0.E[k] - r4.E[k], m22 = r4.D[k] - r0.D[k];
+                sxy[k] = -((m11 + 2.0f * (m12 + m21)) + 4.0f * m22);
+            }
+        }
+    }
+    if (need_sah) {
+        float zx[2], zy[2], g2[2];
+        const float inv1 = (float)p.inv_d1;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            zx[k] = sx[k] * inv1, zy[k] = sy[k] * inv1;
+            g2[k] = fmaf(zx[k], zx[k], zy[k] * zy[k]);
+        }
+        const float ang = p.degrees ? (float)p.rad2deg : 1.0f;
+        if (p.surf_mask & 1u)
+            store2(p.out[0], off, full, nvalid, slope_rad(g2[0]) * ang + car[0], slope_rad(g2[1]) * ang + car[1]);
+        if (p.surf_mask & 2u)
+            store2(p.out[1], off, full, nvalid, aspect_rad(zx[0], zy[0]) * ang + car[0],
+                   aspect_rad(zx[1], zy[1]) * ang + car[1]);
+        if (p.surf_mask & 4u) {
+            const float ky = (float)p.hs_ky, kx = -(float)p.hs_kx, sa = (float)p.hs_sin_alt, zf2 = (float)p.zf2;
+            const float lo = p.clip_hs ? 0.0f : -CUDART_INF_F, hi = p.clip_hs ? 255.0f : CUDART_INF_F;
+            float o[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float r = xb_rsqrt(fmaf(zf2, g2[k], 1.0f));
+                const float inner = fmaf(ky, zy[k], fmaf(kx, zx[k], sa));
+                o[k] = fminf(fmaxf(fmaf(254.0f * r, inner, 1.5f), lo), hi) + car[k];
+            }
+            store2(p.out[2], off, full, nvalid, o[0], o[1]);
+        }
+    }
+    if (p.surf_mask & 8u) {
+        const float f = (float)(-200.0 * p.inv_d2);
+        store2(p.out[3], off, full, nvalid, (sxx[0] + syy[0]) * f + car[0], (sxx[1] + syy[1]) * f + car[1]);
+    }
+    if constexpr (ALG) {
+        if (p.surf_mask & ~15u) {
+            float r6a[6], r6b[6];
+            curv_alg<float>(sx[0], sy[0], sxx[0], syy[0], sxy[0], p, r6a);
+            curv_alg<float>(sx[1], sy[1], sxx[1], syy[1], sxy[1], p, r6b);
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+                if (p.surf_mask & (1u << (4 + a)))
+                    store2(p.out[4 + a], off, full, nvalid, r6a[a] + car[0], r6b[a] + car[1]);
+        }
+    }
+}
+
+template <bool ALG, int OCC>
+__global__ void __launch_bounds__(NTHREADS, OCC)
+florinsky_sliding_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TerrainParams p) {
+    constexpr uint32_t STAGE_BYTES = BOXW * FL_BOXH * sizeof(float);
+    constexpr int STAGE_ELEMS = ((STAGE_BYTES + 127) / 128) * 128 / sizeof(float);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* smem = reinterpret_cast<float*>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar[NSTAGES];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wx = warp & 1, wy = warp >> 1;  // 2 x 4 warps: 64-pixel-wide strips, 15 rows each
+    const long long tiles_x = p.tiles_x, ntiles = p.ntiles, W = p.cols;
+
+    if (tid == 0) {
+        xb_prefetch_tensormap(&tmap);
+#pragma unroll
+        for (int s = 0; s < NSTAGES; ++s) xb_mbar_init(&full_bar[s], 1);
+        xb_fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGES; ++s) {
+            const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+            if (t < ntiles) {
+                const int ty = (int)(t / tiles_x), tx = (int)(t % tiles_x);
+                xb_mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                xb_tma_load_2d(smem + (size_t)s * STAGE_ELEMS, &tmap, &full_bar[s], tx * TW - XOFF,
+                               (int)p.row_begin + ty * FL_TH - 2);
+            }
+        }
+    }
+    const bool need2 = (p.surf_mask & ~7u) != 0;
+    const bool need_sah = (p.surf_mask & 7u) != 0;
+    const bool vec_ok = p.vec_ok != 0;
+
+    int it = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int stage = it % NSTAGES;
+        const int ty = (int)(t / tiles_x), tx = (int)(t % tiles_x);
+        const long long y_tile = p.row_begin + (long long)ty * FL_TH;
+        const long long x0 = (long long)tx * TW + wx * 64 + 2 * lane;
+        float* tile = smem + (size_t)stage * STAGE_ELEMS;
+        xb_mbar_wait(&full_bar[stage], (uint32_t)((it / NSTAGES) & 1));
+
+        const bool active = x0 < W;
+        const bool full = vec_ok && (x0 + 1 < W);
+        const int nvalid = (int)((W - x0) < 2 ? (W - x0) : 2);
+        // first staged row of this warp = tile row wy*15 (i.e. output row - 2); column x0 - 2
+        const float* base = tile + (size_t)(wy * FL_RPW) * BOXW + (XOFF + wx * 64 + 2 * lane - 2);
+        const long long y_first = y_tile + wy * FL_RPW;
+        if (active && y_first < p.row_end) {
+            RowFeat f0, f1, f2, f3, f4;
+            make_features(base + 0 * BOXW, f0);
+            make_features(base + 1 * BOXW, f1);
+            make_features(base + 2 * BOXW, f2);
+            make_features(base + 3 * BOXW, f3);
+            long long off = (y_first - p.row_begin) * p.out_ld + x0;
+            long long y = y_first;
+#pragma unroll 1
+            for (int g = 0; g < FL_RPW / 5; ++g) {
+                const float* rp = base + (size_t)(4 + 5 * g) * BOXW;
+                // five output rows per trip: the ring returns to its starting assignment
+#define XB_FL_STEP(NEW, A, B, C, D, E)                                                   \
+    make_features(rp, NEW);                                                              \
+    if (y < p.row_end) emit_row<ALG>(A, B, C, D, E, p, off, full, nvalid, need2, need_sah); \
+    rp += BOXW, off += p.out_ld, ++y;
+                XB_FL_STEP(f4, f0, f1, f2, f3, f4)
+                XB_FL_STEP(f0, f1, f2, f3, f4, f0)
+                XB_FL_STEP(f1, f2, f3, f4, f0, f1)
+                XB_FL_STEP(f2, f3, f4, f0, f1, f2)
+                XB_FL_STEP(f3, f4, f0, f1, f2, f3)
+#undef XB_FL_STEP
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const long long tn = t + (long long)NSTAGES * gridDim.x;
+            if (tn < ntiles) {
+                const int tyn = (int)(tn / tiles_x), txn = (int)(tn % tiles_x);
+                xb_mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                xb_tma_load_2d(tile, &tmap, &full_bar[stage], txn * TW - XOFF, (int)p.row_begin + tyn * FL_TH - 2);
+            }
+        }
+    }
+}
+
+// Eligibility: float32, Florinsky surface attributes only, 16-byte aligned raster (TMA), no windowed indexes.
+int launch_florinsky_sliding(const TerrainParams& p_in, cudaStream_t stream) {
+    TerrainParams p = p_in;
+    p.tiles_x = (p.cols + TW - 1) / TW;
+    const long long tiles_y = (p.row_end - p.row_begin + FL_TH - 1) / FL_TH;
+    p.ntiles = p.tiles_x * tiles_y;
+    if (p.ntiles <= 0) return XB_OK;
+    int num_sms = 0;
+    int rc = xb_num_sms(&num_sms);
+    if (rc) return rc;
+    bool vec_ok = (p.out_ld * 4) % 8 == 0;  // 8-byte vector stores
+    for (int i = 0; i < 14; ++i)
+        if (p.out[i] && (reinterpret_cast<uintptr_t>(p.out[i]) % 8) != 0) vec_ok = false;
+    p.vec_ok = vec_ok ? 1 : 0;
+    xb_cuTensorMapEncodeTiled_t enc = xb_get_tensormap_encoder();
+    if (!enc) return XB_ERR_UNSUPPORTED;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    cuuint64_t gdim[2] = {(cuuint64_t)p.cols, (cuuint64_t)p.rows_buf};
+    cuuint64_t gstr[1] = {(cuuint64_t)(p.ld * 4)};
+    cuuint32_t box[2] = {(cuuint32_t)BOXW, (cuuint32_t)FL_BOXH};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(p.dem), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
+    if (r != CUDA_SUCCESS) {
+        xb_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return XB_ERR_CUDA;
+    }
+    const size_t smem = (size_t)NSTAGES * (((size_t)BOXW * FL_BOXH * 4 + 127) / 128 * 128);
+    const bool alg = (p.surf_mask & ~15u) != 0;
+    auto launch_one = [&](auto kern) -> int {
+        XB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        XB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTHREADS, smem));
+        if (occ < 1) occ = 1;
+        long long grid = (long long)num_sms * occ;
+        if (grid > p.ntiles) grid = p.ntiles;
+        kern<<<(unsigned)grid, NTHREADS, smem, stream>>>(tmap, p);
+        XB_CUDA_CHECK(cudaGetLastError());
+        return XB_OK;
+    };
+    // 2 CTAs/SM: the 5-row feature ring needs ~100 registers (a 3-CTA build spills and measured 40 % slower)
+    if (alg) return launch_one(florinsky_sliding_kernel<true, 2>);
+    return launch_one(florinsky_sliding_kernel<false, 2>);
+}
+
+}  // namespace xbt
