@@ -1,0 +1,159 @@
+#!/usr/bin/env python
+"""bench_extra.py -- the other two BASELINE.json workloads of the hot path, one JSON line each (not the driver's headline;
+the lines are committed under profiles/):
+
+    python bench_extra.py variogram [--n 1000000] [--cpu-n 40000]     # configs[2]: 1e6 samples, 50 lag bins
+    python bench_extra.py nuthkaab  [--size 16384] [--cpu-size 1024]  # configs[4]: 10 dense iterations
+
+Each line carries the GPU figure (CUDA events / wall clock around the public API), the bound it is compared against and a
+`cpu_baseline` from the oracle (C/OpenMP all-pairs binning; NumPy/SciPy restatement of the reference's iteration)."""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def bench_variogram(args) -> dict:
+    import torch
+
+    from oracle import c_oracle, variogram_oracle as vo
+    from xdem_b200 import _lib, spatialstats as xs
+
+    dev = torch.device("cuda")
+    S, gsd, n_lags = 32768, 5.0, 50
+    g = torch.Generator(device=dev).manual_seed(44)
+    lin = torch.randint(0, S * S, (int(args.n * 1.01),), generator=g, device=dev, dtype=torch.int64).unique()
+    lin = lin[torch.randperm(lin.numel(), generator=g, device=dev)][: args.n]
+    x, y = lin % S, lin // S
+    v = torch.randn(lin.numel(), generator=g, device=dev)
+    maxlag = float(np.hypot(S - 1, S - 1) * gsd)
+    n = lin.numel()
+    pairs = n * (n - 1) // 2
+    times = []
+    for rep in range(args.steps + 1):
+        l0 = _lib.launch_count()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        edges, cnt, ssq = xs.pairwise_lag_binning(x, y, v, None, gsd, n_lags=n_lags, maxlag=maxlag)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+        launches = _lib.launch_count() - l0
+    dt = min(times[1:])
+    assert int(cnt.sum()) == pairs - 1  # every pair binned once; the farthest pair sits on the last (open) edge
+    # CPU baseline: plain-C all-pairs binning (oracle), all threads, bounded N
+    m = args.cpu_n
+    xc = np.stack([(x[:m] * gsd).cpu().numpy().astype(np.float64), (y[:m] * gsd).cpu().numpy().astype(np.float64)], 1)
+    vc = v[:m].cpu().numpy().astype(np.float64)
+    c_oracle.variogram_pairs(xc[:2000], vc[:2000], edges)
+    t0 = time.perf_counter()
+    c_oracle.variogram_pairs(xc, vc, edges)
+    tc = time.perf_counter() - t0
+    sm_clock, sms = 1.965e9, 148
+    issue_peak = sms * 4 * 32 * sm_clock  # thread-instructions / s
+    return {
+        "metric": "Gpairs/s all-pairs empirical variogram (Matheron, 50 even lag bins)", "value": pairs / dt / 1e9,
+        "unit": "Gpairs/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "dtype": "u32 distances / f32 diffs, u64 counts, f64 sums", "data": "synthetic",
+        "config": {"workload": f"sample_empirical_variogram core: {n} random samples of a 32768^2 grid, gsd 5, 50 even "
+                               f"bins, includes Morton sort + max-distance pass + binning ({launches} kernel launches)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "issue (no HBM traffic: 16 MB of samples stay in L2)",
+                     "achieved": pairs / dt * 13 / 1e12, "peak": issue_peak / 1e12, "unit": "T thread-instr/s",
+                     "frac": pairs / dt * 13 / issue_peak,
+                     "note": "13 issue slots per pair (DESIGN.md K2) x pairs/s vs 148 SM x 4 x 32 lanes x 1.965 GHz"},
+        "cpu_baseline": {"value": m * (m - 1) / 2 / tc / 1e9, "unit": "Gpairs/s", "cores": c_oracle.num_threads(),
+                         "kind": "port", "sample": f"first {m} of the same samples ({m*(m-1)//2:.3e} pairs, {tc:.1f} s)",
+                         "what": "oracle/variogram_oracle.c (restated scikit-gstat pairwise binning, C/OpenMP)"},
+    }
+
+
+def bench_nuthkaab(args) -> dict:
+    import torch
+
+    from oracle import nk_oracle
+    from xdem_b200 import _lib, coreg
+
+    dev = torch.device("cuda")
+    size = args.size
+
+    def surf(n, dx, dy, device):
+        yy = torch.arange(n, device=device, dtype=torch.float32)[:, None]
+        xx = torch.arange(n, device=device, dtype=torch.float32)[None, :]
+        z = torch.full((n, n), 1500.0, device=device)
+        rng = np.random.default_rng(45)
+        for _ in range(12):
+            kx, ky = rng.uniform(0.01, 0.12, 2) * rng.choice([-1, 1], 2)
+            amp, ph = rng.uniform(5, 40), rng.uniform(0, 2 * np.pi)
+            z += float(amp) * torch.sin(float(kx) * (xx + dx) + float(ky) * (yy + dy) + float(ph))
+        return z
+
+    g = torch.Generator(device=dev).manual_seed(46)
+    ref = surf(size, 0.0, 0.0, dev)
+    tba = surf(size, 0.37, -0.61, dev) + 1.5 + 0.01 * torch.randn((size, size), generator=g, device=dev)
+    times = []
+    for rep in range(args.steps + 1):
+        l0 = _lib.launch_count()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        (e, n, vz), used = coreg.nuth_kaab(ref, tba, transform=(5.0, 0, 0, 0, -5.0, 0), tolerance=0.0,
+                                           max_iterations=10, params_random={"subsample": 1.0})
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+        launches = _lib.launch_count() - l0
+    dt = min(times[1:])
+    assert abs(e / 5 + 0.37) < 2e-3 and abs(n / 5 + 0.61) < 2e-3 and abs(vz + 1.5) < 2e-3, (e, n, vz)
+    # CPU baseline: NumPy/SciPy restatement of the reference's iteration (same code path as xdem on a CPU)
+    cs = args.cpu_size
+    rc, tc_ = ref[:cs, :cs].cpu().numpy(), tba[:cs, :cs].cpu().numpy()
+    t0 = time.perf_counter()
+    nk_oracle.nuth_kaab(rc, tc_, None, (5.0, -5.0), 0.0, 10)
+    tcpu = time.perf_counter() - t0
+    peak = 6481.1
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    algo = (12 + 10 * 16) * size * size  # aux once + 16 B/px/iteration
+    return {
+        "metric": "Mpixel*iteration/s Nuth-Kaab (dense, 10 iterations)", "value": size * size * 10 / dt / 1e6,
+        "unit": "Mpixel*iter/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "dtype": "f32 rasters, f64 interpolation/moments, exact medians", "data": "synthetic",
+        "config": {"workload": f"NuthKaab {size}^2 ref/tba pair, subsample=1, 10 iterations, 72 aspect bins, host "
+                               f"curve_fit ({launches} kernel launches); recovered shift px "
+                               f"({-e/5:.4f}, {-n/5:.4f}), dz {vz:.4f}"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": algo / dt / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": algo / dt / 1e9 / peak,
+                     "note": "algorithmic minimum 12 B/px (aux) + 16 B/px/iteration; the radix-select medians stream "
+                             "~7 passes per iteration (DESIGN.md K3)"},
+        "cpu_baseline": {"value": cs * cs * 10 / tcpu / 1e6, "unit": "Mpixel*iter/s", "cores": 1, "kind": "port",
+                         "sample": f"{cs}^2 crop of the same pair, 10 iterations ({tcpu:.1f} s)",
+                         "what": "oracle/nk_oracle.py (NumPy/SciPy restatement of affine.py:477-609, pinned to reference "
+                                 "fixtures; the reference itself is single-threaded NumPy here)"},
+    }
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("workload", choices=["variogram", "nuthkaab"])
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--cpu-n", type=int, default=40_000)
+    ap.add_argument("--size", type=int, default=16384)
+    ap.add_argument("--cpu-size", type=int, default=1024)
+    args = ap.parse_args()
+    line = bench_variogram(args) if args.workload == "variogram" else bench_nuthkaab(args)
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -152,19 +152,32 @@ int xb_nk_dh(const float* ref_dev, const float* tba_dev, const uint8_t* sub_mask
              double dx_px, double dy_px, float* dh_dev, uint32_t* asp_minmax_dev, unsigned long long* n_finite_dev,
              void* stream);
 
-/* One MSD radix-select histogram pass over order-preserving float32 keys (exact medians: np.nanmedian(dh),
- * affine.py:504, and the per-aspect-bin nanmedian of y = (dh - vshift)/slope_tan, base.py:1014-1020).
- * mode 0: key = dh, n_groups = 1.  mode 1: key = float32(y), group = aspect bin among n_groups equal-width bins of
- * [asp_lo, asp_hi] (scipy.stats.binned_statistic semantics).  For keys with (key & prefix_mask) == prefix_dev[group]:
- * hist_dev[group*n_digits + ((key >> shift) & (n_digits-1))] += 1.  moments_dev (or NULL): [n, sum y, sum y^2]. */
-int xb_nk_hist(const float* dh_dev, const float* slope_tan_dev, const float* aspect_dev, int64_t n, int mode,
-               double vshift, double asp_lo, double asp_hi, int n_groups, const uint32_t* prefix_dev,
-               uint32_t prefix_mask, int shift, int n_digits, unsigned long long* hist_dev, double* moments_dev,
-               void* stream);
-/* next_key_dev[group] = min(next_key_dev[group], smallest key > sel_dev[group]) -- upper median of even-sized groups. */
-int xb_nk_next(const float* dh_dev, const float* slope_tan_dev, const float* aspect_dev, int64_t n, int mode,
-               double vshift, double asp_lo, double asp_hi, int n_groups, const uint32_t* sel_dev,
-               uint32_t* next_key_dev, void* stream);
+/* Exact medians by MSD radix select on order-preserving float32 keys (np.nanmedian, affine.py:504 and the per-bin
+ * nanmedian of `nd_binning`, base.py:1014-1020 -> spatialstats.py:147-149).
+ *
+ * Global select on dh:  for finite dh with (key & prefix_mask) == prefix:  hist_dev[(key >> shift) & (n_digits-1)] += 1.
+ * xb_nk_next: next_key_dev[0] = min(next_key_dev[0], smallest key > sel)  (upper median of even counts). */
+int xb_nk_hist(const float* dh_dev, int64_t n, uint32_t prefix, uint32_t prefix_mask, int shift, int n_digits,
+               unsigned long long* hist_dev, void* stream);
+int xb_nk_next(const float* dh_dev, int64_t n, uint32_t sel, uint32_t* next_key_dev, void* stream);
+
+/* Grouped select over aspect bins.  xb_nk_make_keys computes once per iteration, for every element, the key of
+ * y = float32((dh - vshift)/slope_tan) (affine.py:381, 505) and its aspect bin among n_groups equal-width bins of
+ * [asp_lo, asp_hi] (scipy.stats.binned_statistic semantics: edges = linspace, right-most edge closed); elements with
+ * non-finite dh or y get group 255.  It also fills the first digit histogram hist_dev[group*n_digits + digit] and
+ * moments_dev = [n, sum y, sum y^2] (p0 of affine.py:384).  bin_cache_dev [n] keeps every pixel's aspect bin; with
+ * reuse_bins != 0 (same [asp_lo, asp_hi] as the call that filled it) the bins are read back instead of recomputed.
+ * xb_nk_hist_keys / xb_nk_next_keys refine on the 5-byte
+ * (key, group) pairs with per-group prefixes / selections. */
+int xb_nk_make_keys(const float* dh_dev, const float* slope_tan_dev, const float* aspect_dev, int64_t n, double vshift,
+                    double asp_lo, double asp_hi, int n_groups, uint32_t* key_dev, uint8_t* group_dev,
+                    uint8_t* bin_cache_dev, int reuse_bins, int shift, int n_digits, unsigned long long* hist_dev,
+                    double* moments_dev, void* stream);
+int xb_nk_hist_keys(const uint32_t* key_dev, const uint8_t* group_dev, int64_t n, int n_groups,
+                    const uint32_t* prefix_dev, uint32_t prefix_mask, int shift, int n_digits,
+                    unsigned long long* hist_dev, void* stream);
+int xb_nk_next_keys(const uint32_t* key_dev, const uint8_t* group_dev, int64_t n, int n_groups,
+                    const uint32_t* sel_dev, uint32_t* next_key_dev, void* stream);
 
 #ifdef __cplusplus
 }

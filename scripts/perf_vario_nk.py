@@ -34,3 +34,17 @@ def nk(size):
     print(f"NuthKaab {size}^2 dense 10 iterations: {dt*1e3:.1f} ms  {size*size*10/dt/1e6:.1f} Mpix*iter/s  shifts {e/5:.4f} {n/5:.4f} {v:.4f}  launches {_lib.launch_count()-l0}", flush=True)
 vario(200_000); vario(1_000_000)
 nk(4096); nk(16384)
+
+def nk_pieces(size=16384):
+    g = torch.Generator(device=dev).manual_seed(45)
+    ref = 1500 + 30 * torch.sin(torch.arange(size, device=dev)[None, :] * 0.05) + 20 * torch.cos(torch.arange(size, device=dev)[:, None] * 0.031) + 0.05 * torch.randn((size, size), generator=g, device=dev)
+    tba = torch.roll(ref, shifts=(0, 0), dims=(0, 1)) + 1.5 + 0.01 * torch.randn((size, size), generator=g, device=dev)
+    st = coreg._NKState(ref.float(), tba.float(), None)
+    def t(f, n=3):
+        f(); torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(n): r = f()
+        torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3, r
+    ms, (lo, hi, nf) = t(lambda: st.compute_dh(0.37, -0.61)); print(f"  dh pass            {ms:8.2f} ms")
+    ms, (med, cnt, _) = t(lambda: st.select_medians(0, 0.0, 0.0, 1.0, 1)); print(f"  global median      {ms:8.2f} ms  ({med[0]:.5f})")
+    ms, r = t(lambda: st.select_medians(1, float(med[0]), lo, hi, 72, want_moments=True)); print(f"  72-bin medians     {ms:8.2f} ms")
+nk_pieces()

@@ -59,11 +59,17 @@ def lib() -> ctypes.CDLL:
     L.xb_nk_dh.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                            c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p]
     L.xb_nk_hist.restype = c_int
-    L.xb_nk_hist.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_double, c_double, c_double, c_int,
-                             c_void_p, c_uint32, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    L.xb_nk_hist.argtypes = [c_void_p, c_int64, c_uint32, c_uint32, c_int, c_int, c_void_p, c_void_p]
     L.xb_nk_next.restype = c_int
-    L.xb_nk_next.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_double, c_double, c_double, c_int,
-                             c_void_p, c_void_p, c_void_p]
+    L.xb_nk_next.argtypes = [c_void_p, c_int64, c_uint32, c_void_p, c_void_p]
+    L.xb_nk_make_keys.restype = c_int
+    L.xb_nk_make_keys.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_int, c_void_p,
+                                  c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    L.xb_nk_hist_keys.restype = c_int
+    L.xb_nk_hist_keys.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_uint32, c_int, c_int, c_void_p,
+                                  c_void_p]
+    L.xb_nk_next_keys.restype = c_int
+    L.xb_nk_next_keys.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]
     _lib = L
     return L
 
@@ -85,6 +91,7 @@ def launch_count() -> int:
 #: every symbol declared in include/xdem_b200.h (checked by tests/test_abi.py)
 EXPORTED = ["xb_last_error", "xb_version", "xb_launch_count", "xb_terrain_fused", "xb_terrain_fused_host",
             "xb_variogram_group_size", "xb_variogram_chunk", "xb_variogram_pairs", "xb_variogram_maxd2", "xb_nk_aux",
-            "xb_nk_dh", "xb_nk_hist", "xb_nk_next", "xb_windowed_generic", "xb_set_option"]
+            "xb_nk_dh", "xb_nk_hist", "xb_nk_next", "xb_nk_make_keys", "xb_nk_hist_keys", "xb_nk_next_keys",
+            "xb_windowed_generic", "xb_set_option"]
 
 __all__ = ["lib", "check", "launch_count", "XdemB200Error", "LIB_PATH", "EXPORTED", "c_int32"]

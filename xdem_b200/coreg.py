@@ -92,73 +92,104 @@ class _NKState:
         lo, hi = (float(v) for v in mmh.view(np.float32))
         return lo, hi, n_fin
 
-    def _hist(self, mode: int, vshift: float, lo: float, hi: float, n_groups: int, prefix: np.ndarray,
-              prefix_mask: int, shift: int, n_digits: int, moments: torch.Tensor | None) -> np.ndarray:
-        hist = torch.zeros(n_groups * n_digits, dtype=torch.int64, device=self.dev)
-        pre = _u32_tensor(prefix, self.dev)
-        with torch.cuda.device(self.dev):
-            _lib.check(self.L.xb_nk_hist(self.dh.data_ptr(), self.slope_tan.data_ptr(), self.aspect.data_ptr(), self.n,
-                                         mode, float(vshift), float(lo), float(hi), n_groups, pre.data_ptr(),
-                                         ctypes.c_uint32(prefix_mask), shift, n_digits, hist.data_ptr(),
-                                         moments.data_ptr() if moments is not None else None, self.stream))
-        self._allreduce(hist)
-        if moments is not None:
-            self._allreduce(moments)
-        return hist.cpu().numpy().reshape(n_groups, n_digits)
-
     def _allreduce(self, t: torch.Tensor, op: Any = None) -> None:
         import torch.distributed as dist
 
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(t, op=op or dist.ReduceOp.SUM, group=self.group)
 
+    def _allreduce_min_u32(self, t_i32: torch.Tensor) -> np.ndarray:
+        """min over ranks of uint32 payloads carried in int32 tensors; returns uint32 host array."""
+        import torch.distributed as dist
+
+        v = t_i32.to(torch.int64) & 0xFFFFFFFF
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.MIN, group=self.group)
+        return v.cpu().numpy().astype(np.uint32)
+
+    @staticmethod
+    def _pick_digit(hist: np.ndarray, rank_in_bucket: np.ndarray, counts: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+        """per group: digit whose cumulative count first exceeds the wanted rank, and the count below that digit."""
+        cum = np.cumsum(hist, axis=1)
+        n_groups, n_digits = hist.shape
+        digit = np.array([int(np.searchsorted(cum[g], rank_in_bucket[g] + 1, side="left")) if counts[g] > 0 else 0
+                          for g in range(n_groups)], dtype=np.int64)
+        digit = np.minimum(digit, n_digits - 1)
+        below = np.where(digit > 0, cum[np.arange(n_groups), np.maximum(digit - 1, 0)], 0)
+        return digit, below
+
     def select_medians(self, mode: int, vshift: float, lo: float, hi: float, n_groups: int,
                        want_moments: bool = False) -> tuple[np.ndarray, np.ndarray, np.ndarray | None]:
-        """Exact per-group medians (np.nanmedian semantics: mean of the two middle values for even counts) of the
-        float32 keys by 3-pass MSD radix select (11 + 11 + 10 bits).  Returns (median float64 [n_groups], count,
-        moments or None)."""
-        passes = [(21, 2048), (10, 2048), (0, 1024)]
+        """Exact medians (np.nanmedian semantics: mean of the two middle values for even counts) of float32 keys by MSD
+        radix select.  mode 0: global median of dh (11 + 11 + 10 bit passes, one shared-memory histogram per CTA).
+        mode 1: per-aspect-bin medians of y = (dh - vshift)/slope_tan: one pass builds compact (key, bin) pairs, the
+        first 8-bit histogram and the moments, three more 8-bit passes stream the 5-byte pairs (n_groups x 256 counters
+        per CTA in shared memory).  Returns (median float64 [n_groups], count, moments or None)."""
+        L, dev, n = self.L, self.dev, self.n
+        moments_t = torch.zeros(3, dtype=torch.float64, device=dev)
+        if mode == 0:
+            passes = [(21, 2048), (10, 2048), (0, 1024)]
+        else:
+            passes = [(24, 256), (16, 256), (8, 256), (0, 256)]
+            if getattr(self, "_keys", None) is None:
+                self._keys = torch.empty(n, dtype=torch.int32, device=dev)
+                self._grp = torch.empty(n, dtype=torch.uint8, device=dev)
+                self._bin_cache = torch.empty(n, dtype=torch.uint8, device=dev)
+                self._bin_range = None
         prefix = np.zeros(n_groups, dtype=np.uint32)
         prefix_mask = 0
-        moments_t = torch.zeros(3, dtype=torch.float64, device=self.dev) if want_moments else None
-        counts = None
-        k_lo = None  # 0-based rank of the lower median inside the still-selected bucket
-        below = np.zeros(n_groups, dtype=np.int64)  # number of keys < selected bucket so far
-        for ip, (shift, n_digits) in enumerate(passes):
-            hist = self._hist(mode, vshift, lo, hi, n_groups, prefix, prefix_mask, shift, n_digits,
-                              moments_t if ip == 0 else None)
-            if ip == 0:
-                counts = hist.sum(axis=1)
-                k_lo = (counts - 1) // 2
-            cum = np.cumsum(hist, axis=1)
-            digit = np.array([int(np.searchsorted(cum[g], k_lo[g] + 1 - below[g], side="left")) if counts[g] > 0 else 0
-                              for g in range(n_groups)], dtype=np.int64)
-            digit = np.minimum(digit, n_digits - 1)
-            below += np.where(digit > 0, cum[np.arange(n_groups), np.maximum(digit - 1, 0)], 0)
-            prefix = (prefix | (digit.astype(np.uint32) << np.uint32(shift))).astype(np.uint32)
-            prefix_mask |= (n_digits - 1) << shift
-            last_hist = hist[np.arange(n_groups), digit]
-        # prefix now holds the exact key of the lower median; `below` keys are smaller, `last_hist` are equal
-        lower = _ordered_to_float(prefix).astype(np.float64)
-        median = lower.copy()
-        even = (counts % 2 == 0) & (counts > 0)
-        need_next = even & (below + last_hist < (counts // 2 + 1))  # upper median is a strictly larger key
-        if need_next.any():
-            sel = _u32_tensor(prefix, self.dev)
-            nxt = _u32_tensor(np.full(n_groups, 0xFFFFFFFF, dtype=np.uint32), self.dev)
-            with torch.cuda.device(self.dev):
-                _lib.check(self.L.xb_nk_next(self.dh.data_ptr(), self.slope_tan.data_ptr(), self.aspect.data_ptr(),
-                                             self.n, mode, float(vshift), float(lo), float(hi), n_groups,
-                                             sel.data_ptr(), nxt.data_ptr(), self.stream))
-            import torch.distributed as dist
-
-            # unsigned order == signed order after flipping the top bit; all-reduce(min) over ranks on that
-            nxt64 = (nxt.to(torch.int64) & 0xFFFFFFFF)
-            self._allreduce(nxt64, op=dist.ReduceOp.MIN if dist.is_available() else None)
-            upper = _ordered_to_float(nxt64.cpu().numpy().astype(np.uint32)).astype(np.float64)
-            median = np.where(need_next, 0.5 * (lower + upper), median)
+        below = np.zeros(n_groups, dtype=np.int64)
+        counts = k_lo = last_hist = None
+        with torch.cuda.device(dev):
+            for ip, (shift, n_digits) in enumerate(passes):
+                hist = torch.zeros(n_groups * n_digits, dtype=torch.int64, device=dev)
+                if mode == 0:
+                    _lib.check(L.xb_nk_hist(self.dh.data_ptr(), n, int(prefix[0]), prefix_mask, shift, n_digits,
+                                            hist.data_ptr(), self.stream))
+                elif ip == 0:
+                    # a pixel's aspect bin only depends on [lo, hi] and n_groups: the kernel caches the bin of every
+                    # pixel, later iterations with an identical range read the cache back
+                    rng_key = (float(lo), float(hi), int(n_groups))
+                    reuse = self._bin_range == rng_key
+                    _lib.check(L.xb_nk_make_keys(self.dh.data_ptr(), self.slope_tan.data_ptr(), self.aspect.data_ptr(),
+                                                 n, float(vshift), float(lo), float(hi), n_groups,
+                                                 self._keys.data_ptr(), self._grp.data_ptr(),
+                                                 self._bin_cache.data_ptr(), int(reuse), shift, n_digits,
+                                                 hist.data_ptr(), moments_t.data_ptr(), self.stream))
+                    self._bin_range = rng_key
+                    self._allreduce(moments_t)
+                else:
+                    pre = _u32_tensor(prefix, dev)
+                    _lib.check(L.xb_nk_hist_keys(self._keys.data_ptr(), self._grp.data_ptr(), n, n_groups,
+                                                 pre.data_ptr(), prefix_mask, shift, n_digits, hist.data_ptr(),
+                                                 self.stream))
+                self._allreduce(hist)
+                h = hist.cpu().numpy().reshape(n_groups, n_digits)
+                if ip == 0:
+                    counts = h.sum(axis=1)
+                    k_lo = (counts - 1) // 2
+                digit, below_d = self._pick_digit(h, k_lo - below, counts)
+                below += below_d
+                prefix = (prefix | (digit.astype(np.uint32) << np.uint32(shift))).astype(np.uint32)
+                prefix_mask |= (n_digits - 1) << shift
+                last_hist = h[np.arange(n_groups), digit]
+            # prefix = exact key of the lower median; `below` keys are smaller, `last_hist` keys are equal to it
+            lower = _ordered_to_float(prefix).astype(np.float64)
+            median = lower.copy()
+            even = (counts % 2 == 0) & (counts > 0)
+            need_next = even & (below + last_hist < (counts // 2 + 1))  # the upper median is a strictly larger key
+            if need_next.any():
+                nxt = _u32_tensor(np.full(n_groups, 0xFFFFFFFF, dtype=np.uint32), dev)
+                if mode == 0:
+                    _lib.check(L.xb_nk_next(self.dh.data_ptr(), n, int(prefix[0]), nxt.data_ptr(), self.stream))
+                else:
+                    sel = _u32_tensor(prefix, dev)
+                    _lib.check(L.xb_nk_next_keys(self._keys.data_ptr(), self._grp.data_ptr(), n, n_groups,
+                                                 sel.data_ptr(), nxt.data_ptr(), self.stream))
+                upper = _ordered_to_float(self._allreduce_min_u32(nxt)).astype(np.float64)
+                median = np.where(need_next, 0.5 * (lower + upper), median)
         median = np.where(counts > 0, median, np.nan)
-        moments = moments_t.cpu().numpy() if moments_t is not None else None
+        moments = moments_t.cpu().numpy() if (want_moments and mode == 1) else None
         return median, counts, moments
 
 

@@ -34,9 +34,8 @@ __global__ void __launch_bounds__(NT)
 nk_aux_kernel(const float* __restrict__ z, long long rows_buf, long long cols, long long ld, int top_is_border,
               int bottom_is_border, long long row_begin, long long row_end, float* __restrict__ slope_tan,
               float* __restrict__ aspect, long long out_ld) {
-    const long long n = (row_end - row_begin) * cols;
-    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
-        const long long r = row_begin + i / cols, c = i % cols;
+    for (long long r = row_begin + blockIdx.x; r < row_end; r += gridDim.x)
+    for (long long c = threadIdx.x; c < cols; c += NT) {
         const float* zr = z + r * ld;
         float gx, gy;
         if (c == 0)
@@ -78,9 +77,9 @@ nk_dh_kernel(const float* __restrict__ ref, const float* __restrict__ tba, const
              unsigned long long* __restrict__ n_finite) {
     unsigned lmin = 0xffffffffu, lmax = 0u;
     unsigned long long cnt = 0;
-    const long long n = rows * cols;
-    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
-        const long long r = i / cols, c = i % cols;
+    // one CTA walks whole rows (no 64-bit div/mod per element)
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x)
+    for (long long c = threadIdx.x; c < cols; c += NT) {
         float out = CUDART_NAN_F;
         if (sub_mask[r * cols + c]) {
             // tba buffer row index of raster row (r + i0): local shard rows start at raster row tba_row0
@@ -123,109 +122,188 @@ nk_dh_kernel(const float* __restrict__ ref, const float* __restrict__ tba, const
 // np.digitize semantics, the right-most edge belongs to the last bin.
 __device__ __forceinline__ int aspect_bin(float a, double lo, double hi, double step, double inv_step, int n_bins) {
     const double x = (double)a;
-    int k = (int)floor((x - lo) * inv_step);
+    const double t = (x - lo) * inv_step;
+    int k = (int)t;  // t >= 0 for in-range data
     k = max(0, min(n_bins - 1, k));
+    const double frac = t - (double)k;
+    if (frac > 1e-7 && frac < 1.0 - 1e-7) return k;  // far from an edge: the estimate is the digitize() result
+    // near an edge: compare with the edges exactly as NumPy builds them (linspace: k*step + lo, last edge = hi)
     while (k > 0 && x < __dadd_rn(__dmul_rn((double)k, step), lo)) --k;
     while (k < n_bins - 1) {
-        const double e = (k + 1 == n_bins) ? hi : __dadd_rn(__dmul_rn((double)(k + 1), step), lo);
+        const double e = __dadd_rn(__dmul_rn((double)(k + 1), step), lo);
         if (x >= e) ++k; else break;
     }
     return k;
 }
 
-struct KeyGroup {
-    unsigned key;
-    int group;
-    bool ok;
-    double y;
-};
-
-// mode 0: key = dh (one group).  mode 1: key = float32((dh - vshift)/slope_tan) (affine.py:381, 505), group = aspect bin.
-__device__ __forceinline__ KeyGroup make_key(int mode, float dhv, const float* __restrict__ slope_tan,
-                                             const float* __restrict__ aspect, long long i, double vshift,
-                                             double asp_lo, double asp_hi, double step, double inv_step, int n_groups) {
-    KeyGroup kg;
-    kg.ok = isfinite(dhv);
-    kg.group = 0;
-    kg.key = 0;
-    kg.y = 0.0;
-    if (!kg.ok) return kg;
-    if (mode == 0) {
-        kg.key = ordered_key(dhv);
-        return kg;
-    }
-    const double y = ((double)dhv - vshift) / (double)slope_tan[i];
-    const float yf = (float)y;
-    kg.ok = isfinite(yf);
-    if (!kg.ok) return kg;
-    kg.y = y;
-    kg.key = ordered_key(yf);
-    kg.group = aspect_bin(aspect[i], asp_lo, asp_hi, step, inv_step, n_groups);
-    return kg;
+// y key of one element: float32((dh - vshift) / slope_tan) (affine.py:381, 505).  The subtraction is done in float64
+// like the reference, the division in IEEE float32 (the key is a float32 anyway; <= 1 ulp from rounding the float64
+// quotient).  Returns false for non-finite results.
+__device__ __forceinline__ bool y_key(float dhv, float st, double vshift, unsigned& key, float& yf) {
+    if (!isfinite(dhv)) return false;
+    yf = __fdiv_rn((float)((double)dhv - vshift), st);
+    if (!isfinite(yf)) return false;
+    key = ordered_key(yf);
+    return true;
 }
 
-// One MSD radix-select pass: for keys whose bits under prefix_mask equal prefix[group]: hist[group][digit]++ with
-// digit = (key >> shift) & (n_digits-1).  moments (mode 1, first pass): [n, sum y, sum y^2] for p0 (affine.py:384).
+// ---- global select on dh (np.nanmedian(dh), affine.py:504): per-CTA shared-memory histogram of one digit ----------
 __global__ void __launch_bounds__(NT)
-nk_hist_kernel(const float* __restrict__ dh, const float* __restrict__ slope_tan, const float* __restrict__ aspect,
-               long long n, int mode, double vshift, double asp_lo, double asp_hi, int n_groups,
-               const unsigned* __restrict__ prefix, unsigned prefix_mask, int shift, int n_digits,
-               unsigned long long* __restrict__ hist, double* __restrict__ moments) {
-    extern __shared__ unsigned sh_hist[];  // n_digits counters when n_groups == 1
-    const bool use_smem = (n_groups == 1);
-    if (use_smem) {
-        for (int k = threadIdx.x; k < n_digits; k += NT) sh_hist[k] = 0u;
-        __syncthreads();
+nk_hist_kernel(const float* __restrict__ dh, long long n, unsigned prefix, unsigned prefix_mask, int shift,
+               int n_digits, unsigned long long* __restrict__ hist) {
+    extern __shared__ unsigned sh_hist[];
+    for (int k = threadIdx.x; k < n_digits; k += NT) sh_hist[k] = 0u;
+    __syncthreads();
+    // 4 independent coalesced loads in flight per thread (memory-level parallelism), then the shared-memory updates
+    const long long stride = (long long)gridDim.x * NT;
+    for (long long i0 = (long long)blockIdx.x * NT + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (i0 + u * stride < n) ? dh[i0 + u * stride] : CUDART_NAN_F;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!isfinite(v[u])) continue;
+            const unsigned key = ordered_key(v[u]);
+            if ((key & prefix_mask) != prefix) continue;
+            atomicAdd(&sh_hist[(key >> shift) & (unsigned)(n_digits - 1)], 1u);
+        }
     }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_digits; k += NT)
+        if (sh_hist[k]) atomicAdd(&hist[k], (unsigned long long)sh_hist[k]);
+}
+
+__global__ void __launch_bounds__(NT)
+nk_next_kernel(const float* __restrict__ dh, long long n, unsigned sel, unsigned* __restrict__ next_key) {
+    unsigned best = 0xffffffffu;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+        const float v = dh[i];
+        if (!isfinite(v)) continue;
+        const unsigned key = ordered_key(v);
+        if (key > sel) best = min(best, key);
+    }
+    best = __reduce_min_sync(0xffffffffu, best);
+    if ((threadIdx.x & 31) == 0 && best != 0xffffffffu) atomicMin(next_key, best);
+}
+
+// ---- grouped select (72-bin nanmedian of y over aspect, base.py:1014-1020) -----------------------------------------
+// Pass 0 computes, once per iteration, the compact (key, group) pair of every element (group 255 = excluded), the first
+// digit histogram (per-CTA shared memory: n_groups x n_digits counters) and the moments [n, sum y, sum y^2] of y for the
+// initial guess p0 (affine.py:384).  Later passes stream only the 5-byte pairs.
+__global__ void __launch_bounds__(NT)
+nk_make_keys_kernel(const float* __restrict__ dh, const float* __restrict__ slope_tan, const float* __restrict__ aspect,
+                    unsigned char* __restrict__ grp_cache,
+                    long long n, double vshift, double asp_lo, double asp_hi, int n_groups,
+                    unsigned* __restrict__ key_out, unsigned char* __restrict__ grp_out, int reuse_groups, int shift,
+                    int n_digits, unsigned long long* __restrict__ hist, double* __restrict__ moments) {
+    extern __shared__ unsigned sh_hist[];
+    const int n_cnt = n_groups * n_digits;
+    for (int k = threadIdx.x; k < n_cnt; k += NT) sh_hist[k] = 0u;
+    __syncthreads();
     const double step = (asp_hi - asp_lo) / (double)n_groups;
     const double inv_step = step > 0.0 ? 1.0 / step : 0.0;
     double m0 = 0.0, m1 = 0.0, m2 = 0.0;
-    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
-        const KeyGroup kg = make_key(mode, dh[i], slope_tan, aspect, i, vshift, asp_lo, asp_hi, step, inv_step, n_groups);
-        if (!kg.ok) continue;
-        if (moments) {
-            m0 += 1.0;
-            m1 += kg.y;
-            m2 += kg.y * kg.y;
-        }
-        if ((kg.key & prefix_mask) != prefix[kg.group]) continue;
-        const unsigned digit = (kg.key >> shift) & (unsigned)(n_digits - 1);
-        if (use_smem)
-            atomicAdd(&sh_hist[digit], 1u);
-        else
-            atomicAdd(&hist[(long long)kg.group * n_digits + digit], 1ull);
-    }
-    if (use_smem) {
-        __syncthreads();
-        for (int k = threadIdx.x; k < n_digits; k += NT)
-            if (sh_hist[k]) atomicAdd(&hist[k], (unsigned long long)sh_hist[k]);
-    }
-    if (moments) {
+    const long long stride = (long long)gridDim.x * NT;
+    for (long long i0 = (long long)blockIdx.x * NT + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        float dv[4], sv[4], av[4];
+        unsigned char bv[4];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            m0 += __shfl_xor_sync(0xffffffffu, m0, o);
-            m1 += __shfl_xor_sync(0xffffffffu, m1, o);
-            m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+        for (int u = 0; u < 4; ++u) {
+            const long long i = i0 + u * stride;
+            const bool in = i < n;
+            dv[u] = in ? dh[i] : CUDART_NAN_F;
+            sv[u] = in ? slope_tan[i] : CUDART_NAN_F;
+            av[u] = (in && !reuse_groups) ? aspect[i] : CUDART_NAN_F;
+            bv[u] = (in && reuse_groups) ? grp_cache[i] : (unsigned char)255;
         }
-        if ((threadIdx.x & 31) == 0 && m0 > 0.0) {
-            atomicAdd(&moments[0], m0);
-            atomicAdd(&moments[1], m1);
-            atomicAdd(&moments[2], m2);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long i = i0 + u * stride;
+            if (i >= n) break;
+            unsigned key = 0u;
+            float yf = 0.f;
+            unsigned char grp = 255;
+            // a pixel's aspect bin only depends on [asp_lo, asp_hi]: it is computed for EVERY pixel with a finite
+            // aspect (valid or not this iteration) and cached; later iterations with the same range read it back
+            unsigned char bin = bv[u];
+            if (!reuse_groups) {
+                bin = isfinite(av[u]) ? (unsigned char)aspect_bin(av[u], asp_lo, asp_hi, step, inv_step, n_groups)
+                                      : (unsigned char)255;
+                grp_cache[i] = bin;
+            }
+            if (y_key(dv[u], sv[u], vshift, key, yf) && bin != 255) {
+                grp = bin;
+                m0 += 1.0;
+                m1 += (double)yf;
+                m2 += (double)yf * (double)yf;
+                atomicAdd(&sh_hist[(int)grp * n_digits + (int)((key >> shift) & (unsigned)(n_digits - 1))], 1u);
+            }
+            key_out[i] = key;
+            grp_out[i] = grp;
         }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_cnt; k += NT)
+        if (sh_hist[k]) atomicAdd(&hist[k], (unsigned long long)sh_hist[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m0 += __shfl_xor_sync(0xffffffffu, m0, o);
+        m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+        m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+    }
+    if ((threadIdx.x & 31) == 0 && m0 > 0.0) {
+        atomicAdd(&moments[0], m0);
+        atomicAdd(&moments[1], m1);
+        atomicAdd(&moments[2], m2);
     }
 }
 
-// smallest ordered key strictly greater than sel[group] (for the upper median of even-sized groups)
 __global__ void __launch_bounds__(NT)
-nk_next_kernel(const float* __restrict__ dh, const float* __restrict__ slope_tan, const float* __restrict__ aspect,
-               long long n, int mode, double vshift, double asp_lo, double asp_hi, int n_groups,
-               const unsigned* __restrict__ sel, unsigned* __restrict__ next_key) {
-    const double step = (asp_hi - asp_lo) / (double)n_groups;
-    const double inv_step = step > 0.0 ? 1.0 / step : 0.0;
-    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
-        const KeyGroup kg = make_key(mode, dh[i], slope_tan, aspect, i, vshift, asp_lo, asp_hi, step, inv_step, n_groups);
-        if (!kg.ok) continue;
-        if (kg.key > sel[kg.group]) atomicMin(&next_key[kg.group], kg.key);
+nk_hist_keys_kernel(const unsigned* __restrict__ key, const unsigned char* __restrict__ grp, long long n, int n_groups,
+                    const unsigned* __restrict__ prefix, unsigned prefix_mask, int shift, int n_digits,
+                    unsigned long long* __restrict__ hist) {
+    extern __shared__ unsigned sh_hist[];
+    const int n_cnt = n_groups * n_digits;
+    for (int k = threadIdx.x; k < n_cnt; k += NT) sh_hist[k] = 0u;
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * NT;
+    for (long long i0 = (long long)blockIdx.x * NT + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        unsigned g[4], k[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool in = i0 + u * stride < n;
+            g[u] = in ? grp[i0 + u * stride] : 255u;
+            k[u] = in ? key[i0 + u * stride] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (g[u] >= (unsigned)n_groups) continue;
+            if ((k[u] & prefix_mask) != prefix[g[u]]) continue;
+            atomicAdd(&sh_hist[g[u] * n_digits + ((k[u] >> shift) & (unsigned)(n_digits - 1))], 1u);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_cnt; k += NT)
+        if (sh_hist[k]) atomicAdd(&hist[k], (unsigned long long)sh_hist[k]);
+}
+
+__global__ void __launch_bounds__(NT)
+nk_next_keys_kernel(const unsigned* __restrict__ key, const unsigned char* __restrict__ grp, long long n, int n_groups,
+                    const unsigned* __restrict__ sel, unsigned* __restrict__ next_key) {
+    const long long stride = (long long)gridDim.x * NT;
+    for (long long i0 = (long long)blockIdx.x * NT + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        unsigned g[4], k[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool in = i0 + u * stride < n;
+            g[u] = in ? grp[i0 + u * stride] : 255u;
+            k[u] = in ? key[i0 + u * stride] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (g[u] >= (unsigned)n_groups) continue;
+            if (k[u] > sel[g[u]] && k[u] < next_key[g[u]]) atomicMin(&next_key[g[u]], k[u]);
+        }
     }
 }
 
@@ -289,34 +367,92 @@ int xb_nk_dh(const float* ref_dev, const float* tba_dev, const uint8_t* sub_mask
     return XB_OK;
 }
 
-int xb_nk_hist(const float* dh_dev, const float* slope_tan_dev, const float* aspect_dev, int64_t n, int mode,
-               double vshift, double asp_lo, double asp_hi, int n_groups, const uint32_t* prefix_dev,
-               uint32_t prefix_mask, int shift, int n_digits, unsigned long long* hist_dev, double* moments_dev,
-               void* stream) {
-    if (!dh_dev || !prefix_dev || !hist_dev || n <= 0 || n_groups < 1 || n_digits < 2 || (n_digits & (n_digits - 1)) ||
-        n_digits > 4096 || (mode != 0 && mode != 1) || (mode == 1 && (!slope_tan_dev || !aspect_dev)) ||
-        (mode == 0 && n_groups != 1)) {
+int xb_nk_hist(const float* dh_dev, int64_t n, uint32_t prefix, uint32_t prefix_mask, int shift, int n_digits,
+               unsigned long long* hist_dev, void* stream) {
+    if (!dh_dev || !hist_dev || n <= 0 || n_digits < 2 || (n_digits & (n_digits - 1)) || n_digits > 4096) {
         xb_set_error("bad arguments to xb_nk_hist");
         return XB_ERR_INVALID;
     }
-    const size_t smem = n_groups == 1 ? (size_t)n_digits * sizeof(unsigned) : 0;
-    xbn::nk_hist_kernel<<<xbn::grid_for(n, 8), xbn::NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        dh_dev, slope_tan_dev, aspect_dev, n, mode, vshift, asp_lo, asp_hi, n_groups, prefix_dev, prefix_mask, shift,
-        n_digits, hist_dev, moments_dev);
+    xbn::nk_hist_kernel<<<xbn::grid_for(n, 8), xbn::NT, (size_t)n_digits * sizeof(unsigned),
+                          reinterpret_cast<cudaStream_t>(stream)>>>(dh_dev, n, prefix, prefix_mask, shift, n_digits,
+                                                                    hist_dev);
     XB_CUDA_CHECK(cudaGetLastError());
     xb_count_launch(1);
     return XB_OK;
 }
 
-int xb_nk_next(const float* dh_dev, const float* slope_tan_dev, const float* aspect_dev, int64_t n, int mode,
-               double vshift, double asp_lo, double asp_hi, int n_groups, const uint32_t* sel_dev,
-               uint32_t* next_key_dev, void* stream) {
-    if (!dh_dev || !sel_dev || !next_key_dev || n <= 0 || n_groups < 1 || (mode != 0 && mode != 1)) {
+int xb_nk_next(const float* dh_dev, int64_t n, uint32_t sel, uint32_t* next_key_dev, void* stream) {
+    if (!dh_dev || !next_key_dev || n <= 0) {
         xb_set_error("bad arguments to xb_nk_next");
         return XB_ERR_INVALID;
     }
-    xbn::nk_next_kernel<<<xbn::grid_for(n, 8), xbn::NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        dh_dev, slope_tan_dev, aspect_dev, n, mode, vshift, asp_lo, asp_hi, n_groups, sel_dev, next_key_dev);
+    xbn::nk_next_kernel<<<xbn::grid_for(n, 8), xbn::NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dh_dev, n, sel,
+                                                                                                      next_key_dev);
+    XB_CUDA_CHECK(cudaGetLastError());
+    xb_count_launch(1);
+    return XB_OK;
+}
+
+static int grouped_smem(int n_groups, int n_digits, size_t* smem) {
+    if (n_groups < 1 || n_groups > 254 || n_digits < 2 || (n_digits & (n_digits - 1)) ||
+        (size_t)n_groups * n_digits * sizeof(unsigned) > 160 * 1024) {
+        xb_set_error("grouped select needs 1..254 groups and n_groups*n_digits*4 <= 160 KiB (got %d x %d)", n_groups,
+                     n_digits);
+        return XB_ERR_INVALID;
+    }
+    *smem = (size_t)n_groups * n_digits * sizeof(unsigned);
+    return XB_OK;
+}
+
+int xb_nk_make_keys(const float* dh_dev, const float* slope_tan_dev, const float* aspect_dev, int64_t n, double vshift,
+                    double asp_lo, double asp_hi, int n_groups, uint32_t* key_dev, uint8_t* group_dev,
+                    uint8_t* bin_cache_dev, int reuse_bins, int shift, int n_digits, unsigned long long* hist_dev,
+                    double* moments_dev, void* stream) {
+    size_t smem = 0;
+    if (!dh_dev || !slope_tan_dev || !aspect_dev || !key_dev || !group_dev || !bin_cache_dev || !hist_dev ||
+        !moments_dev || n <= 0) {
+        xb_set_error("bad arguments to xb_nk_make_keys");
+        return XB_ERR_INVALID;
+    }
+    int rc = grouped_smem(n_groups, n_digits, &smem);
+    if (rc) return rc;
+    XB_CUDA_CHECK(cudaFuncSetAttribute(xbn::nk_make_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    xbn::nk_make_keys_kernel<<<xbn::grid_for(n, smem > 72 * 1024 ? 1 : (smem > 36 * 1024 ? 3 : 6)), xbn::NT, smem,
+                               reinterpret_cast<cudaStream_t>(stream)>>>(
+        dh_dev, slope_tan_dev, aspect_dev, bin_cache_dev, n, vshift, asp_lo, asp_hi, n_groups, key_dev, group_dev,
+        reuse_bins ? 1 : 0, shift, n_digits, hist_dev, moments_dev);
+    XB_CUDA_CHECK(cudaGetLastError());
+    xb_count_launch(1);
+    return XB_OK;
+}
+
+int xb_nk_hist_keys(const uint32_t* key_dev, const uint8_t* group_dev, int64_t n, int n_groups,
+                    const uint32_t* prefix_dev, uint32_t prefix_mask, int shift, int n_digits,
+                    unsigned long long* hist_dev, void* stream) {
+    size_t smem = 0;
+    if (!key_dev || !group_dev || !prefix_dev || !hist_dev || n <= 0) {
+        xb_set_error("bad arguments to xb_nk_hist_keys");
+        return XB_ERR_INVALID;
+    }
+    int rc = grouped_smem(n_groups, n_digits, &smem);
+    if (rc) return rc;
+    XB_CUDA_CHECK(cudaFuncSetAttribute(xbn::nk_hist_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    xbn::nk_hist_keys_kernel<<<xbn::grid_for(n, smem > 72 * 1024 ? 1 : (smem > 36 * 1024 ? 3 : 6)), xbn::NT, smem,
+                               reinterpret_cast<cudaStream_t>(stream)>>>(key_dev, group_dev, n, n_groups, prefix_dev,
+                                                                         prefix_mask, shift, n_digits, hist_dev);
+    XB_CUDA_CHECK(cudaGetLastError());
+    xb_count_launch(1);
+    return XB_OK;
+}
+
+int xb_nk_next_keys(const uint32_t* key_dev, const uint8_t* group_dev, int64_t n, int n_groups,
+                    const uint32_t* sel_dev, uint32_t* next_key_dev, void* stream) {
+    if (!key_dev || !group_dev || !sel_dev || !next_key_dev || n <= 0 || n_groups < 1 || n_groups > 254) {
+        xb_set_error("bad arguments to xb_nk_next_keys");
+        return XB_ERR_INVALID;
+    }
+    xbn::nk_next_keys_kernel<<<xbn::grid_for(n, 8), xbn::NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        key_dev, group_dev, n, n_groups, sel_dev, next_key_dev);
     XB_CUDA_CHECK(cudaGetLastError());
     xb_count_launch(1);
     return XB_OK;
