@@ -118,14 +118,24 @@ int xb_windowed_generic(const void* dem_dev, int dtype, int64_t rows_buf, int64_
  *               unit_prefix[i] = number of units of rows < i.  [unit_begin, unit_end) is this call's share of the units
  *               (multi-GPU: ranks take disjoint ranges and all-reduce count/sumsq, 2*n_bins*8 bytes)
  *  wide         0: d2 fits 32 bits (raster diagonal^2 < 2^32), 1: 64-bit distances
+ *  estimator    0: sumsq accumulates (v_i - v_j)^2 (Matheron); 1: sumsq accumulates |v_i - v_j|^0.5 (Cressie-Hawkins)
  *  count_dev    uint64 [n_bins] and sumsq_dev double [n_bins], accumulated into (caller zeroes them)
  */
 int xb_variogram_group_size(void);
 int xb_variogram_chunk(void);
 int xb_variogram_pairs(const int32_t* pts_dev, const int32_t* gbox_dev, int64_t n_groups,
                        const unsigned long long* edge2_dev, int n_bins, const int64_t* unit_prefix_dev,
-                       int64_t unit_begin, int64_t unit_end, int wide, unsigned long long* count_dev,
+                       int64_t unit_begin, int64_t unit_end, int wide, int estimator, unsigned long long* count_dev,
                        double* sumsq_dev, void* stream);
+/* One radix-select pass for Dowd's estimator (per-class median of |v_i - v_j|, skgstat.estimators.dowd): keys are the
+ * float32 bit patterns of |diff|.  mode 0: for pairs of class k with (key & prefix_mask) == prefix_dev[k]:
+ * hist_dev[k*256 + ((key >> shift) & 255)] += 1.  mode 1: next_key_dev[k] = min(next_key_dev[k], smallest key >
+ * prefix_dev[k]).  Same sample / unit conventions as xb_variogram_pairs. */
+int xb_variogram_median_pass(const int32_t* pts_dev, const int32_t* gbox_dev, int64_t n_groups,
+                              const unsigned long long* edge2_dev, int n_bins, const int64_t* unit_prefix_dev,
+                              int64_t unit_begin, int64_t unit_end, int mode, const uint32_t* prefix_dev,
+                              uint32_t prefix_mask, int shift, unsigned long long* hist_dev, uint32_t* next_key_dev,
+                              void* stream);
 /* Largest squared pixel distance over all sample pairs, accumulated with max into maxd2_dev[0] (skgstat's "even"
  * binning clips maxlag to the largest sampled distance). */
 int xb_variogram_maxd2(const int32_t* pts_dev, const int32_t* gbox_dev, int64_t n_groups,
@@ -151,6 +161,12 @@ int xb_nk_dh(const float* ref_dev, const float* tba_dev, const uint8_t* sub_mask
              int64_t rows, int64_t cols, int64_t ld, int64_t tba_ld, int64_t tba_row0, int64_t tba_rows_total,
              double dx_px, double dy_px, float* dh_dev, uint32_t* asp_minmax_dev, unsigned long long* n_finite_dev,
              void* stream);
+
+/* Translation-only `Coreg.apply` (base.py:1567-1570 shifts the transform; base.py:1755-1760 regrids on the original
+ * grid with `_reproject_horizontal_shift_samecrs`): dst[r,c] = bilinear(src at (r + dy_px, c + dx_px)) + dz, NaN rule as
+ * xb_nk_dh.  For a fitted NuthKaab: dx_px = -shift_x / transform.a, dy_px = -shift_y / transform.e, dz = shift_z. */
+int xb_shift_resample(const float* src_dev, int64_t rows, int64_t cols, int64_t ld, double dx_px, double dy_px,
+                      double dz, float* dst_dev, int64_t dst_ld, void* stream);
 
 /* Exact medians by MSD radix select on order-preserving float32 keys (np.nanmedian, affine.py:504 and the per-bin
  * nanmedian of `nd_binning`, base.py:1014-1020 -> spatialstats.py:147-149).

@@ -48,9 +48,24 @@ def even_bins(distances_max: float, n_lags: int, maxlag: float | None) -> np.nda
     return np.linspace(0, maxlag, n_lags + 1)[1:]
 
 
+def _estimate(x: np.ndarray, estimator: str) -> float:
+    """skgstat.estimators (1.0.x): matheron, cressie (Cressie-Hawkins), dowd."""
+    if x.size == 0:
+        return np.nan
+    if estimator == "matheron":
+        return float(np.sum(x**2) / (2.0 * x.size))
+    if estimator == "cressie":
+        n = x.size
+        return float(np.power((1.0 / n) * np.sum(np.power(x, 0.5)), 4) / (2 * (0.457 + (0.494 / n) + (0.045 / n**2))))
+    if estimator == "dowd":
+        return float(2.198 * np.nanmedian(x) ** 2 / 2)
+    raise NotImplementedError(estimator)
+
+
 def empirical_variogram(coords: np.ndarray, values: np.ndarray, bin_func: object = "even", n_lags: int = 10,
-                        maxlag: float | None = None) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """(bins, exp, count) of skgstat.Variogram(...).get_empirical() / .bin_count with the Matheron estimator.
+                        maxlag: float | None = None, estimator: str = "matheron"
+                        ) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(bins, exp, count) of skgstat.Variogram(...).get_empirical() / .bin_count.
     O(N^2) memory: use for N <= ~2e4 (oracle/c_oracle.variogram_pairs is the big-N checker)."""
     coords = np.asarray(coords, dtype=np.float64)
     values = np.asarray(values, dtype=np.float64)
@@ -73,6 +88,5 @@ def empirical_variogram(coords: np.ndarray, values: np.ndarray, bin_func: object
     for k in range(len(bins)):
         x = diff[groups == k]
         count[k] = x.size
-        if x.size:
-            exp[k] = np.sum(x**2) / (2.0 * x.size)
+        exp[k] = _estimate(x, estimator)
     return bins, exp, count

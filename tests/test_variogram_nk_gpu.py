@@ -197,3 +197,56 @@ def test_nk_subsample_and_large() -> None:
     assert sx == pytest.approx(-0.83 * 2.0, abs=0.02) and sy == pytest.approx(-0.42 * 2.0, abs=0.02)
     assert sz == pytest.approx(2.0, abs=0.02)
     assert nkc.meta["outputs"]["random"]["subsample_final"] == 200000
+
+
+def test_nk_apply_translation() -> None:
+    """`apply`: regrid of the shifted DEM on the input grid == map_coordinates restatement; after
+    applying the fitted shift the residual dh median is ~0 and a second fit finds (almost) no shift."""
+    from scipy.ndimage import map_coordinates
+
+    from xdem_b200 import coreg
+
+    g = parity.load_golden("nk_reference.npz")
+    tr = tuple(g["transform"])
+    nkc = coreg.NuthKaab(max_iterations=8, subsample=1.0).fit(g["ref"], g["tba"], inlier_mask=g["inlier"], transform=tr)
+    sx, sy, sz = nkc.to_translations()
+    applied, tr2 = nkc.apply(g["tba"], transform=tr)
+    assert tr2 == tr and applied.dtype == np.float32 and applied.shape == g["tba"].shape
+    rows, cols = np.mgrid[0:g["tba"].shape[0], 0:g["tba"].shape[1]].astype(np.float64)
+    expect = map_coordinates(g["tba"].astype(np.float64), [rows - sy / tr[4], cols - sx / tr[0]], order=1,
+                             mode="constant", cval=np.nan, prefilter=False) + sz
+    assert np.array_equal(np.isnan(applied), np.isnan(expect))
+    assert np.nanmax(np.abs(applied - expect)) < 3e-4
+    resid = g["ref"] - applied
+    assert abs(np.nanmedian(resid)) < 0.01
+    nk2 = coreg.NuthKaab(max_iterations=5, subsample=1.0).fit(g["ref"], applied, inlier_mask=g["inlier"], transform=tr)
+    assert all(abs(v) < 0.05 for v in nk2.to_translations())
+    shifted, tr3 = nkc.apply(g["tba"], transform=tr, resample=False)
+    assert np.allclose(shifted, g["tba"] + sz, equal_nan=True) and tr3[2] == tr[2] + sx and tr3[5] == tr[5] + sy
+
+
+@pytest.mark.parametrize("estimator", ["cressie", "dowd"])
+@pytest.mark.parametrize("n", [2500, 257])
+def test_robust_estimators_vs_oracle(estimator: str, n: int) -> None:
+    """Cressie-Hawkins and Dowd against the restated scikit-gstat estimators."""
+    import torch
+
+    from oracle import variogram_oracle as vo
+    from xdem_b200 import spatialstats as xs
+
+    shape, gsd = (260, 260), 5.0
+    vals, idx = _sample(shape, n, 91)
+    vals = (vals * 3).astype(np.float32)
+    coords = vo.grid_coords(shape, gsd)
+    maxlag = float(np.hypot(259 * gsd, 259 * gsd))
+    edges_in = np.asarray(vo.default_bins(gsd, maxlag))
+    b_o, exp_o, cnt_o = vo.empirical_variogram(coords[idx], vals.ravel()[idx], edges_in, estimator=estimator)
+    ti = torch.from_numpy(idx).cuda()
+    edges, cnt, third = xs.pairwise_lag_binning(ti % 260, ti // 260, torch.from_numpy(vals.ravel()).cuda()[ti],
+                                                edges_in, gsd, estimator=estimator)
+    assert np.array_equal(cnt, cnt_o)
+    exp = xs.estimate_from_sums(cnt, third, estimator)
+    assert np.allclose(exp, exp_o, rtol=2e-5, equal_nan=True), (exp, exp_o)
+    df = xs.sample_empirical_variogram(vals, gsd=gsd, subsample=600, subsample_method="pdist_point", random_state=3,
+                                       estimator=estimator)
+    assert np.isfinite(df["exp"].values[df["count"].values > 0]).all()

@@ -49,7 +49,10 @@ def lib() -> ctypes.CDLL:
     L.xb_variogram_chunk.restype = c_int
     L.xb_variogram_pairs.restype = c_int
     L.xb_variogram_pairs.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int,
-                                     c_void_p, c_void_p, c_void_p]
+                                     c_int, c_void_p, c_void_p, c_void_p]
+    L.xb_variogram_median_pass.restype = c_int
+    L.xb_variogram_median_pass.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int64, c_int64,
+                                           c_int, c_void_p, c_uint32, c_int, c_void_p, c_void_p, c_void_p]
     L.xb_variogram_maxd2.restype = c_int
     L.xb_variogram_maxd2.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
     L.xb_nk_aux.restype = c_int
@@ -58,6 +61,9 @@ def lib() -> ctypes.CDLL:
     L.xb_nk_dh.restype = c_int
     L.xb_nk_dh.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                            c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.xb_shift_resample.restype = c_int
+    L.xb_shift_resample.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_double, c_double, c_double, c_void_p,
+                                    c_int64, c_void_p]
     L.xb_nk_hist.restype = c_int
     L.xb_nk_hist.argtypes = [c_void_p, c_int64, c_uint32, c_uint32, c_int, c_int, c_void_p, c_void_p]
     L.xb_nk_next.restype = c_int
@@ -90,8 +96,8 @@ def launch_count() -> int:
 
 #: every symbol declared in include/xdem_b200.h (checked by tests/test_abi.py)
 EXPORTED = ["xb_last_error", "xb_version", "xb_launch_count", "xb_terrain_fused", "xb_terrain_fused_host",
-            "xb_variogram_group_size", "xb_variogram_chunk", "xb_variogram_pairs", "xb_variogram_maxd2", "xb_nk_aux",
+            "xb_variogram_group_size", "xb_variogram_chunk", "xb_variogram_pairs", "xb_variogram_median_pass", "xb_variogram_maxd2", "xb_nk_aux",
             "xb_nk_dh", "xb_nk_hist", "xb_nk_next", "xb_nk_make_keys", "xb_nk_hist_keys", "xb_nk_next_keys",
-            "xb_windowed_generic", "xb_set_option"]
+            "xb_windowed_generic", "xb_set_option", "xb_shift_resample"]
 
 __all__ = ["lib", "check", "launch_count", "XdemB200Error", "LIB_PATH", "EXPORTED", "c_int32"]

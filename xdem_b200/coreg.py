@@ -363,6 +363,37 @@ class NuthKaab:
         self._fit_called = True
         return self
 
+    def apply(self, elev: Any, bias_vars: Any = None, resample: bool = True, resampling: str = "linear",
+              transform: Any = None, crs: Any = None, z_name: str = "z", **kwargs: Any) -> tuple[Any, Any]:
+        """Apply the estimated translation to a DEM (``Coreg.apply`` -> ``apply_matrix``, base.py:1686-1766, for a
+        translation-only matrix): returns ``(applied_dem, transform)``.  With ``resample=True`` (default) the shifted DEM
+        is bilinearly regridded on the input grid (GPU, `xb_shift_resample`); with ``resample=False`` only the vertical
+        shift is added and the returned transform is translated (base.py:1567-1570)."""
+        if not self._fit_called:
+            raise AssertionError(".fit() does not seem to have been called yet")
+        if resampling not in ("linear", "bilinear"):
+            raise NotImplementedError("the B200 apply step implements bilinear resampling only")
+        if _arrays.is_raster_like(elev):
+            transform = transform or elev.transform
+            elev = elev.data
+        sx, sy, sz = self.to_translations()
+        a, e = _transform_coeffs(transform)
+        t, kind = _arrays.to_device(elev)
+        if t.dtype != torch.float32:
+            t = t.to(torch.float32)
+        if not resample:
+            out = t + sz
+            tr = tuple(transform) if transform is not None else None
+            new_tr = (tr[0], tr[1], tr[2] + sx, tr[3], tr[4], tr[5] + sy) if tr is not None else None
+            return _arrays.from_device(out, kind), new_tr
+        t = t.contiguous()
+        out = torch.empty_like(t)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+        with torch.cuda.device(t.device):
+            _lib.check(_lib.lib().xb_shift_resample(t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), -sx / a,
+                                                    -sy / e, float(sz), out.data_ptr(), out.stride(0), stream))
+        return _arrays.from_device(out, kind), transform
+
     def to_matrix(self) -> np.ndarray:
         """affine.py:2532-2541."""
         matrix = np.diag(np.ones(4, dtype=float))

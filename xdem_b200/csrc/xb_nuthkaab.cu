@@ -307,6 +307,33 @@ nk_next_keys_kernel(const unsigned* __restrict__ key, const unsigned char* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Translation-only `apply` (base.py:1567-1570, 1755-1760): dst = bilinear(src at (row + dy, col + dx)) + dz, same 2x2
+// fixed-weight stencil and NaN rule as nk_dh_kernel (the regrid of `_reproject_horizontal_shift_samecrs`).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+shift_resample_kernel(const float* __restrict__ src, long long rows, long long cols, long long ld, long long i0,
+                      long long j0, double w00, double w01, double w10, double w11, double dz,
+                      float* __restrict__ dst, long long dst_ld) {
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x)
+    for (long long c = threadIdx.x; c < cols; c += NT) {
+        const long long rr = r + i0, cc = c + j0;
+        double acc = CUDART_NAN;
+        if (rr >= 0 && rr + 1 < rows && cc >= 0 && cc + 1 < cols) {
+            const float* t = src + rr * ld + cc;
+            acc = w00 * (double)t[0] + w01 * (double)t[1] + w10 * (double)t[ld] + w11 * (double)t[ld + 1];
+        } else if (rr >= 0 && rr < rows && cc >= 0 && cc < cols) {
+            const bool row_ok = (rr + 1 < rows), col_ok = (cc + 1 < cols);
+            const float* t = src + rr * ld + cc;
+            acc = w00 * (double)t[0];
+            acc += col_ok ? w01 * (double)t[1] : (w01 != 0.0 ? CUDART_NAN : 0.0);
+            acc += row_ok ? w10 * (double)t[ld] : (w10 != 0.0 ? CUDART_NAN : 0.0);
+            acc += (row_ok && col_ok) ? w11 * (double)t[ld + 1] : (w11 != 0.0 ? CUDART_NAN : 0.0);
+        }
+        dst[r * dst_ld + c] = (float)(acc + dz);
+    }
+}
+
 static int grid_for(long long n, int per_sm) {
     int sms = 0;
     if (xb_num_sms(&sms)) sms = 148;
@@ -362,6 +389,23 @@ int xb_nk_dh(const float* ref_dev, const float* tba_dev, const uint8_t* sub_mask
     xbn::nk_dh_kernel<<<xbn::grid_for(n, 16), xbn::NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         ref_dev, tba_dev, sub_mask_dev, aspect_dev, rows, cols, ld, tba_ld, tba_row0, tba_rows_total, (long long)fi,
         (long long)fj, w00, w01, w10, w11, dh_dev, asp_minmax_dev, n_finite_dev);
+    XB_CUDA_CHECK(cudaGetLastError());
+    xb_count_launch(1);
+    return XB_OK;
+}
+
+int xb_shift_resample(const float* src_dev, int64_t rows, int64_t cols, int64_t ld, double dx_px, double dy_px,
+                      double dz, float* dst_dev, int64_t dst_ld, void* stream) {
+    if (!src_dev || !dst_dev || rows <= 0 || cols <= 0 || ld < cols || dst_ld < cols || !isfinite(dx_px) ||
+        !isfinite(dy_px) || fabs(dx_px) > 1e9 || fabs(dy_px) > 1e9) {
+        xb_set_error("bad arguments to xb_shift_resample");
+        return XB_ERR_INVALID;
+    }
+    const double fi = floor(dy_px), fj = floor(dx_px);
+    const double fy = dy_px - fi, fx = dx_px - fj;
+    xbn::shift_resample_kernel<<<xbn::grid_for(rows * cols, 16), xbn::NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        src_dev, rows, cols, ld, (long long)fi, (long long)fj, (1.0 - fy) * (1.0 - fx), (1.0 - fy) * fx,
+        fy * (1.0 - fx), fy * fx, dz, dst_dev, dst_ld);
     XB_CUDA_CHECK(cudaGetLastError());
     xb_count_launch(1);
     return XB_OK;

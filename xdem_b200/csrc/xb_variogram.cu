@@ -80,7 +80,7 @@ __device__ __forceinline__ unsigned long long clamp_edge<unsigned long long>(uns
 }
 
 // One sweep of a 128 x 128 tile over the 3 lag classes [b, b+3).
-template <typename D2, bool CHECK>
+template <typename D2, bool CHECK, int EST>
 __device__ __forceinline__ void sweep_tile(const int4* __restrict__ sj, const int (&xi)[IPL], const int (&yi)[IPL],
                                            const float (&vi)[IPL], const int (&ii)[IPL], bool diag, D2 L, D2 Ta, D2 Tb,
                                            D2 Tc, unsigned (&cnt)[3], float (&sum)[3]) {
@@ -92,7 +92,8 @@ __device__ __forceinline__ void sweep_tile(const int4* __restrict__ sj, const in
         for (int m = 0; m < IPL; ++m) {
             const D2 d2 = dist2<D2>(pj.x - xi[m], pj.y - yi[m]);
             const float df = vj - vi[m];
-            const float q = df * df;
+            // Matheron: sum (v_i - v_j)^2;  Cressie-Hawkins: sum |v_i - v_j|^(1/2)   (skgstat.estimators)
+            const float q = EST == 0 ? df * df : sqrtf(fabsf(df));
             bool ok = d2 >= L;
             if (CHECK) ok = ok && (pj.w >= 0) && (ii[m] >= 0) && (!diag || ii[m] < pj.w);
             const bool p0 = ok && (d2 < Ta);
@@ -114,7 +115,7 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
     return v;
 }
 
-template <typename D2>
+template <typename D2, int EST>
 __global__ void __launch_bounds__(NTHREADS, 2)
 variogram_pairs_kernel(const int4* __restrict__ pts, const int4* __restrict__ gbox, int G,
                        const unsigned long long* __restrict__ edge2, int n_bins,
@@ -173,9 +174,9 @@ variogram_pairs_kernel(const int4* __restrict__ pts, const int4* __restrict__ gb
                 unsigned cnt[3] = {0u, 0u, 0u};
                 float sum[3] = {0.f, 0.f, 0.f};
                 if (check)
-                    sweep_tile<D2, true>(sj, xi, yi, vi, ii, diag, L, Ta, Tb, Tc, cnt, sum);
+                    sweep_tile<D2, true, EST>(sj, xi, yi, vi, ii, diag, L, Ta, Tb, Tc, cnt, sum);
                 else
-                    sweep_tile<D2, false>(sj, xi, yi, vi, ii, diag, L, Ta, Tb, Tc, cnt, sum);
+                    sweep_tile<D2, false, EST>(sj, xi, yi, vi, ii, diag, L, Ta, Tb, Tc, cnt, sum);
 #pragma unroll
                 for (int s = 0; s < 3; ++s) {
                     const unsigned c = __reduce_add_sync(0xffffffffu, cnt[s]);
@@ -187,6 +188,92 @@ variogram_pairs_kernel(const int4* __restrict__ pts, const int4* __restrict__ gb
                     }
                 }
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dowd's estimator needs the per-class MEDIAN of |v_i - v_j| (skgstat.estimators.dowd): exact selection by MSD radix
+// select on the float32 bit pattern of |diff| (non-negative floats order like their bits), 4 passes of 8 bits.  One
+// pass = one sweep over all pairs; the class of a pair comes from the same tile thresholds as above, the digit
+// histogram (n_bins x 256 counters) is shared by the CTA in shared memory and flushed once.  MODE 1 finds, per class,
+// the smallest key strictly greater than sel[class] (upper median of even-sized classes).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename D2, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 2)
+variogram_median_kernel(const int4* __restrict__ pts, const int4* __restrict__ gbox, int G,
+                        const unsigned long long* __restrict__ edge2, int n_bins,
+                        const long long* __restrict__ unit_prefix, long long unit_begin, long long unit_end,
+                        unsigned long long* __restrict__ work_counter, const unsigned* __restrict__ prefix,
+                        unsigned prefix_mask, int shift, unsigned long long* __restrict__ hist,
+                        unsigned* __restrict__ next_key) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    int4* sj_all = reinterpret_cast<int4*>(dyn_smem);
+    unsigned* sh = reinterpret_cast<unsigned*>(dyn_smem + (size_t)NWARPS * GS * sizeof(int4));
+    const int n_cnt = MODE == 0 ? n_bins * 256 : n_bins;
+    for (int k = threadIdx.x; k < n_cnt; k += NTHREADS) sh[k] = MODE == 0 ? 0u : 0xffffffffu;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int4* sj = sj_all + (size_t)warp * GS;
+    const unsigned long long edge_last = edge2[n_bins - 1];
+    for (;;) {
+        long long u = 0;
+        if (lane == 0) u = unit_begin + (long long)atomicAdd(work_counter, 1ull);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= unit_end) break;
+        int lo = 0, hi = G;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (unit_prefix[mid] <= u) lo = mid; else hi = mid;
+        }
+        const int gi = lo;
+        const int j_begin = gi + (int)(u - unit_prefix[gi]) * CHUNK_J;
+        const int j_end = min(G, j_begin + CHUNK_J);
+        int xi[IPL], yi[IPL], ii[IPL];
+        float vi[IPL];
+#pragma unroll
+        for (int m = 0; m < IPL; ++m) {
+            const int4 p = pts[(long long)gi * GS + lane + 32 * m];
+            xi[m] = p.x, yi[m] = p.y, vi[m] = __int_as_float(p.z), ii[m] = p.w;
+        }
+        const int4 ibox = gbox[gi];
+        for (int gj = j_begin; gj < j_end; ++gj) {
+            unsigned long long dmin2, dmax2;
+            box_dist2(ibox, gbox[gj], dmin2, dmax2);
+            if (dmin2 >= edge_last) continue;
+            const int b_lo = first_bin_above(edge2, n_bins, dmin2, lane);
+            int b_hi = first_bin_above(edge2, n_bins, dmax2, lane);
+            if (b_hi > n_bins - 1) b_hi = n_bins - 1;
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < IPL; ++m) sj[lane + 32 * m] = pts[(long long)gj * GS + lane + 32 * m];
+            __syncwarp();
+            const bool diag = (gj == gi);
+            for (int jj = 0; jj < GS; ++jj) {
+                const int4 pj = sj[jj];
+                const float vj = __int_as_float(pj.z);
+#pragma unroll
+                for (int m = 0; m < IPL; ++m) {
+                    const unsigned long long d2 = dist2<unsigned long long>(pj.x - xi[m], pj.y - yi[m]);
+                    if (pj.w < 0 || ii[m] < 0 || (diag && ii[m] >= pj.w) || d2 >= edge_last) continue;
+                    int b = b_lo;  // the tile touches only classes b_lo..b_hi (usually <= 3)
+                    while (b < b_hi && d2 >= edge2[b]) ++b;
+                    const unsigned key = __float_as_uint(fabsf(vj - vi[m]));
+                    if (MODE == 0) {
+                        if ((key & prefix_mask) == prefix[b]) atomicAdd(&sh[b * 256 + ((key >> shift) & 255u)], 1u);
+                    } else {
+                        if (key > prefix[b] && key < sh[b]) atomicMin(&sh[b], key);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_cnt; k += NTHREADS) {
+        if (MODE == 0) {
+            if (sh[k]) atomicAdd(&hist[k], (unsigned long long)sh[k]);
+        } else {
+            if (sh[k] != 0xffffffffu) atomicMin(&next_key[k], sh[k]);
         }
     }
 }
@@ -266,7 +353,7 @@ int xb_variogram_chunk(void) { return xbv::CHUNK_J; }
 
 int xb_variogram_pairs(const int32_t* pts_dev, const int32_t* gbox_dev, int64_t n_groups,
                        const unsigned long long* edge2_dev, int n_bins, const int64_t* unit_prefix_dev,
-                       int64_t unit_begin, int64_t unit_end, int wide, unsigned long long* count_dev,
+                       int64_t unit_begin, int64_t unit_end, int wide, int estimator, unsigned long long* count_dev,
                        double* sumsq_dev, void* stream) {
     if (!pts_dev || !gbox_dev || !edge2_dev || !unit_prefix_dev || !count_dev || !sumsq_dev || n_groups <= 0 ||
         n_bins <= 0 || n_groups > 0x7fffffff) {
@@ -287,15 +374,65 @@ int xb_variogram_pairs(const int32_t* pts_dev, const int32_t* gbox_dev, int64_t 
     const int4* pts = reinterpret_cast<const int4*>(pts_dev);
     const int4* gbox = reinterpret_cast<const int4*>(gbox_dev);
     const long long* pref = reinterpret_cast<const long long*>(unit_prefix_dev);
-    if (wide)
-        xbv::variogram_pairs_kernel<unsigned long long><<<(unsigned)grid, xbv::NTHREADS, 0, st>>>(
-            pts, gbox, (int)n_groups, edge2_dev, n_bins, pref, unit_begin, unit_end, xbv::g_counter, count_dev,
-            sumsq_dev);
-    else
-        xbv::variogram_pairs_kernel<unsigned><<<(unsigned)grid, xbv::NTHREADS, 0, st>>>(
-            pts, gbox, (int)n_groups, edge2_dev, n_bins, pref, unit_begin, unit_end, xbv::g_counter, count_dev,
-            sumsq_dev);
+    if (estimator != 0 && estimator != 1) {
+        xb_set_error("estimator must be 0 (matheron: sum of squares) or 1 (cressie: sum of |diff|^0.5)");
+        return XB_ERR_INVALID;
+    }
+#define XB_VG_LAUNCH(D2T, EST)                                                                                     \
+    xbv::variogram_pairs_kernel<D2T, EST><<<(unsigned)grid, xbv::NTHREADS, 0, st>>>(                                \
+        pts, gbox, (int)n_groups, edge2_dev, n_bins, pref, unit_begin, unit_end, xbv::g_counter, count_dev, sumsq_dev)
+    if (wide) {
+        if (estimator) XB_VG_LAUNCH(unsigned long long, 1); else XB_VG_LAUNCH(unsigned long long, 0);
+    } else {
+        if (estimator) XB_VG_LAUNCH(unsigned, 1); else XB_VG_LAUNCH(unsigned, 0);
+    }
+#undef XB_VG_LAUNCH
     XB_CUDA_CHECK(cudaGetLastError());
+    xb_count_launch(1);
+    return XB_OK;
+}
+
+int xb_variogram_median_pass(const int32_t* pts_dev, const int32_t* gbox_dev, int64_t n_groups,
+                              const unsigned long long* edge2_dev, int n_bins, const int64_t* unit_prefix_dev,
+                              int64_t unit_begin, int64_t unit_end, int mode, const uint32_t* prefix_dev,
+                              uint32_t prefix_mask, int shift, unsigned long long* hist_dev, uint32_t* next_key_dev,
+                              void* stream) {
+    if (!pts_dev || !gbox_dev || !edge2_dev || !unit_prefix_dev || !prefix_dev || n_groups <= 0 || n_bins <= 0 ||
+        n_groups > 0x7fffffff || (mode == 0 && !hist_dev) || (mode == 1 && !next_key_dev) || (mode != 0 && mode != 1)) {
+        xb_set_error("bad arguments to xb_variogram_median_pass");
+        return XB_ERR_INVALID;
+    }
+    const size_t smem = (size_t)xbv::NWARPS * xbv::GS * sizeof(int4) + (size_t)(mode == 0 ? n_bins * 256 : n_bins) * 4;
+    if (smem > 200 * 1024) {
+        xb_set_error("too many lag classes for the shared-memory histogram (%d)", n_bins);
+        return XB_ERR_UNSUPPORTED;
+    }
+    if (unit_end <= unit_begin) return XB_OK;
+    int rc = xbv::ensure_counter();
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    XB_CUDA_CHECK(cudaMemsetAsync(xbv::g_counter, 0, sizeof(unsigned long long), st));
+    int num_sms = 0;
+    rc = xb_num_sms(&num_sms);
+    if (rc) return rc;
+    const long long units = unit_end - unit_begin;
+    long long grid = std::min<long long>((long long)num_sms * (smem > 100 * 1024 ? 1 : 2),
+                                         (units + xbv::NWARPS - 1) / xbv::NWARPS);
+    if (grid < 1) grid = 1;
+    const int4* pts = reinterpret_cast<const int4*>(pts_dev);
+    const int4* gbox = reinterpret_cast<const int4*>(gbox_dev);
+    const long long* pref = reinterpret_cast<const long long*>(unit_prefix_dev);
+    auto launch = [&](auto kern) -> int {
+        XB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)grid, xbv::NTHREADS, smem, st>>>(pts, gbox, (int)n_groups, edge2_dev, n_bins, pref, unit_begin,
+                                                          unit_end, xbv::g_counter, prefix_dev, prefix_mask, shift,
+                                                          hist_dev, next_key_dev);
+        XB_CUDA_CHECK(cudaGetLastError());
+        return XB_OK;
+    };
+    rc = mode == 0 ? launch(xbv::variogram_median_kernel<unsigned long long, 0>)
+                   : launch(xbv::variogram_median_kernel<unsigned long long, 1>);
+    if (rc) return rc;
     xb_count_launch(1);
     return XB_OK;
 }

@@ -96,12 +96,14 @@ def _unit_prefix(n_groups: int) -> np.ndarray:
 
 
 def pairwise_lag_binning(x: torch.Tensor, y: torch.Tensor, v: torch.Tensor, edges: np.ndarray | None, gsd: float,
-                         n_lags: int | None = None, maxlag: float | None = None, group: Any = None
-                         ) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+                         n_lags: int | None = None, maxlag: float | None = None, group: Any = None,
+                         estimator: str = "matheron") -> tuple[np.ndarray, np.ndarray, np.ndarray]:
     """All-pairs lag binning of N grid samples (integer pixel coordinates x, y; float32 values v) on the GPU.
 
     ``edges`` = float64 right bin edges, or None for skgstat's "even" binning with ``n_lags`` classes over
-    [0, min(maxlag, largest sampled distance)].  Returns (edges, count int64, sumsq float64).
+    [0, min(maxlag, largest sampled distance)].  Returns (edges, count int64, third) where ``third`` is, per class,
+    sum (v_i-v_j)^2 for "matheron", sum |v_i-v_j|^0.5 for "cressie", or the exact median of |v_i-v_j| for "dowd"
+    (4 radix-select passes over all pairs).
     If torch.distributed is initialised, the work units are split across ranks and count / sumsq all-reduced."""
     import torch.distributed as dist
 
@@ -141,12 +143,73 @@ def pairwise_lag_binning(x: torch.Tensor, y: torch.Tensor, v: torch.Tensor, edge
         u1 = n_units * (rank + 1) // world
         count = torch.zeros(len(edges), dtype=torch.int64, device=dev)
         sumsq = torch.zeros(len(edges), dtype=torch.float64, device=dev)
+        if estimator not in ("matheron", "cressie", "dowd"):
+            raise NotImplementedError(f"estimator '{estimator}'")
         _lib.check(L.xb_variogram_pairs(pts.data_ptr(), gbox.data_ptr(), n_groups, e2.data_ptr(), len(edges),
-                                        prefix.data_ptr(), u0, u1, wide, count.data_ptr(), sumsq.data_ptr(), stream))
+                                        prefix.data_ptr(), u0, u1, wide, 1 if estimator == "cressie" else 0,
+                                        count.data_ptr(), sumsq.data_ptr(), stream))
         if world > 1:
             dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
             dist.all_reduce(sumsq, op=dist.ReduceOp.SUM, group=group)
-    return edges, count.cpu().numpy(), sumsq.cpu().numpy()
+        count_h = count.cpu().numpy()
+        if estimator != "dowd":
+            return edges, count_h, sumsq.cpu().numpy()
+        # Dowd: exact per-class median of |diff| by MSD radix select (8 bits per pass) over all pairs
+        nb = len(edges)
+        pre = np.zeros(nb, dtype=np.uint32)
+        mask = 0
+        below = np.zeros(nb, dtype=np.int64)
+        k_lo = (count_h - 1) // 2
+        last = np.zeros(nb, dtype=np.int64)
+
+        def u32(a: np.ndarray) -> torch.Tensor:
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint32).view(np.int32).copy()).to(dev)
+
+        for shift in (24, 16, 8, 0):
+            hist = torch.zeros(nb * 256, dtype=torch.int64, device=dev)
+            _lib.check(L.xb_variogram_median_pass(pts.data_ptr(), gbox.data_ptr(), n_groups, e2.data_ptr(), nb,
+                                                  prefix.data_ptr(), u0, u1, 0, u32(pre).data_ptr(), mask, shift,
+                                                  hist.data_ptr(), None, stream))
+            if world > 1:
+                dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+            h = hist.cpu().numpy().reshape(nb, 256)
+            cum = np.cumsum(h, axis=1)
+            digit = np.array([int(np.searchsorted(cum[g], k_lo[g] - below[g] + 1, side="left")) if count_h[g] > 0
+                              else 0 for g in range(nb)], dtype=np.int64)
+            digit = np.minimum(digit, 255)
+            below += np.where(digit > 0, cum[np.arange(nb), np.maximum(digit - 1, 0)], 0)
+            pre = (pre | (digit.astype(np.uint32) << np.uint32(shift))).astype(np.uint32)
+            mask |= 255 << shift
+            last = h[np.arange(nb), digit]
+        lower = pre.view(np.float32).astype(np.float64)
+        median = lower.copy()
+        need = (count_h % 2 == 0) & (count_h > 0) & (below + last < (count_h // 2 + 1))
+        if need.any():
+            nxt = u32(np.full(nb, 0xFFFFFFFF, dtype=np.uint32))
+            _lib.check(L.xb_variogram_median_pass(pts.data_ptr(), gbox.data_ptr(), n_groups, e2.data_ptr(), nb,
+                                                  prefix.data_ptr(), u0, u1, 1, u32(pre).data_ptr(), 0, 0, None,
+                                                  nxt.data_ptr(), stream))
+            nx = nxt.to(torch.int64) & 0xFFFFFFFF
+            if world > 1:
+                dist.all_reduce(nx, op=dist.ReduceOp.MIN, group=group)
+            upper = nx.cpu().numpy().astype(np.uint32).view(np.float32).astype(np.float64)
+            median = np.where(need, 0.5 * (lower + upper), median)
+        median = np.where(count_h > 0, median, np.nan)
+    return edges, count_h, median
+
+
+def estimate_from_sums(count: np.ndarray, third: np.ndarray, estimator: str) -> np.ndarray:
+    """skgstat.estimators (1.0.x): matheron = sum d^2 / (2n); cressie = (mean |d|^0.5)^4 / (2 (0.457 + 0.494/n +
+    0.045/n^2)); dowd = 2.198 median(|d|)^2 / 2.  NaN for empty classes."""
+    n = count.astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if estimator == "matheron":
+            exp = third / (2.0 * n)
+        elif estimator == "cressie":
+            exp = np.power(third / n, 4) / (2.0 * (0.457 + 0.494 / n + 0.045 / n**2))
+        else:
+            exp = 2.198 * third**2 / 2.0
+    return np.where(count > 0, exp, np.nan)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -194,9 +257,10 @@ def sample_empirical_variogram(
     ``xdem.spatialstats.sample_empirical_variogram``.
 
     GPU path: ``subsample_method="pdist_point"`` on a 2-D array / Raster-like / CUDA tensor with ``gsd`` (every pair of
-    the random subsample is compared).  Supported skgstat keywords: ``estimator="matheron"`` (default), ``bin_func`` =
-    iterable of right edges (default: the reference's sqrt(2)-geometric edges) or ``"even"`` with ``n_lags``, ``maxlag``.
-    The disk / ring / equidistant samplers and the robust estimators raise NotImplementedError.
+    the random subsample is compared).  Supported skgstat keywords: ``estimator`` in {"matheron" (default), "cressie",
+    "dowd"} (xDEM's uncertainty pipeline passes "dowd", spatialstats.py:1810), ``bin_func`` = iterable of right edges
+    (default: the reference's sqrt(2)-geometric edges) or ``"even"`` with ``n_lags``, ``maxlag``.
+    The disk / ring / equidistant samplers (scikit-gstat metric spaces) raise NotImplementedError.
     """
     if _arrays.is_raster_like(values):
         gsd = values.res[0]
@@ -232,8 +296,8 @@ def sample_empirical_variogram(
     if coords is not None:
         raise NotImplementedError("the B200 variogram path takes a 2-D array + gsd (grid samples)")
     estimator = kwargs.get("estimator", "matheron")
-    if estimator != "matheron":
-        raise NotImplementedError(f"estimator='{estimator}' is not on the B200 hot path yet (only 'matheron')")
+    if estimator not in ("matheron", "cressie", "dowd"):
+        raise NotImplementedError(f"estimator='{estimator}' is not on the B200 hot path (matheron, cressie, dowd)")
     unknown = set(kwargs) - {"estimator", "bin_func", "n_lags", "maxlag"}
     if unknown:
         raise NotImplementedError(f"unsupported skgstat keyword(s) for the B200 variogram path: {sorted(unknown)}")
@@ -284,9 +348,9 @@ def sample_empirical_variogram(
         x = idx % nx
         y = idx // nx
         v = flat[idx]
-        edges, count, sumsq = pairwise_lag_binning(x, y, v, edges_in, gsd, n_lags=n_lags, maxlag=maxlag)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            exp = np.where(count > 0, sumsq / (2.0 * count), np.nan)  # skgstat matheron
+        edges, count, third = pairwise_lag_binning(x, y, v, edges_in, gsd, n_lags=n_lags, maxlag=maxlag,
+                                                   estimator=estimator)
+        exp = estimate_from_sums(count, third, estimator)
         runs.append(pd.DataFrame().assign(exp=exp, bins=edges, count=count))
 
     df = pd.concat(runs)
