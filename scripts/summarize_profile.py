@@ -58,10 +58,30 @@ for name, key in ((f"prof_{TAG}_florinsky4_32768", "florinsky_32768"), (f"prof_{
     lines.append(f"-> DRAM traffic per launch {rd + wr:.4e} B (read {rd:.4e} + write {wr:.4e}); algorithmic 20 B/px x {px} px = {20*px:.4e} B; ratio {(rd+wr)/(20*px):.3f}")
     lines.append(f"-> under ncu (cold, serialised): {dur*1e3:.3f} ms, {(rd+wr)/dur/1e9:.0f} GB/s DRAM; thread-instructions/pixel = {float(d['smsp__inst_executed.sum'][0])*32/px:.1f}")
     traffic[key] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr, "source": f"profiles/ncu_{TAG}.txt ({name})"}
+# K2 / K3 captures: one block per kernel launch in the report
+for name in (f"prof_{TAG}_variogram", f"prof_{TAG}_nuthkaab"):
+    rep = os.path.join(GO, name + ".ncu-rep")
+    if not os.path.exists(rep):
+        continue
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    lines.append(f"\n## {name}\n")
+    short = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+             "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+             "launch__registers_per_thread", "launch__grid_size"]
+    for r in rows[2:]:
+        d = {h: (v, u) for h, u, v in zip(hdr, units, r)}
+        lines.append("kernel " + d.get("Kernel Name", ("?", ""))[0][:110])
+        for w in short:
+            if w in d:
+                lines.append(f"    {w:80s} {d[w][0]:>18s} {d[w][1]}")
 open(os.path.join(PR, f"ncu_{TAG}.txt"), "w").write("\n".join(lines) + "\n")
 json.dump(traffic, open(tpath, "w"), indent=1)
 for f in (f"launches_{TAG}.csv", f"bench_{TAG}.json", f"bench_{TAG}_zt.json", f"bench_{TAG}_horn.json",
-          f"bench_{TAG}_reference.json", f"perf_probe_{TAG}.txt", f"perf_vario_nk_{TAG}.txt"):
+          f"bench_{TAG}_reference.json", f"perf_probe_{TAG}.txt", f"perf_vario_nk_{TAG}.txt",
+          f"bench_{TAG}_variogram.json", f"bench_{TAG}_nuthkaab.json"):
     src = os.path.join(GO, f)
     if os.path.exists(src):
         shutil.copy(src, os.path.join(PR, f))
