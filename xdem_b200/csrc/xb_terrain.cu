@@ -323,7 +323,7 @@ terrain_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                 if (p.win_mask) {
                     constexpr int WS = 2 * HW + 1;
                     constexpr int OFF = H - HW;  // window centred in the tile window
-                    T tpi[4], tri[4], rough[4], rug[4];
+                    T tpi[4], tri[4], rough[4], rug[4], car_w[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const T c = win[H][H + k];
@@ -334,6 +334,7 @@ terrain_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 #pragma unroll
                             for (int cc = 0; cc < WS; ++cc) s = Num<T>::add(s, win[OFF + r][OFF + cc + k]);
                         const T carr = Num<T>::mul(s, T(0));
+                        car_w[k] = carr;
                         const T nm1 = (T)(WS * WS - 1);
                         // TPI = c - (sum - c)/(n-1)  (window.py:216-220)
                         tpi[k] = Num<T>::add(Num<T>::sub(c, Num<T>::div(Num<T>::sub(s, c), nm1)), carr);
@@ -370,34 +371,45 @@ terrain_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                                 }
                             rough[k] = Num<T>::add(Num<T>::sub(mx, mn), carr);  // window.py:281-287
                         }
-                        if constexpr (HW == 1) {
-                            if (p.win_mask & 8u) {
+                    }
+                    if constexpr (HW == 1) {
+                        if (p.win_mask & 8u) {
+                            // own loop over the 4 pixels: one basic block, so segment lengths shared by neighbouring
+                            // pixels (identical expressions) are computed once
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const T c = win[H][H + k];
+                                const T carr = car_w[k];
                                 // Rugosity, Jenness (2004): window.py:598-683 -- 16 half segment lengths, 8 Heron areas
                                 const T z0 = win[OFF + 0][OFF + 0 + k], z1 = win[OFF + 0][OFF + 1 + k],
                                         z2 = win[OFF + 0][OFF + 2 + k], z3 = win[OFF + 1][OFF + 0 + k],
                                         z5 = win[OFF + 1][OFF + 2 + k], z6 = win[OFF + 2][OFF + 0 + k],
                                         z7 = win[OFF + 2][OFF + 1 + k], z8 = win[OFF + 2][OFF + 2 + k];
-                                const T l2d = (T)p.rug_dl2_diag, l2s = (T)p.rug_dl2_straight, l2e = (T)p.rug_dl2_edge;
+                                // straight centre segments and ring segments have the same planimetric length L
+                                // (window.py:628-651); differences are always taken left-right / top-bottom (the
+                                // half-length only depends on dz^2) so that segments shared by neighbouring pixels are
+                                // the same expression and are computed once per thread row.
+                                const T l2d = (T)p.rug_dl2_diag, l2s = (T)p.rug_dl2_straight;
                                 auto hsl = [](T dz, T l2) {
                                     return Num<T>::mul(Num<T>::sqrt(Num<T>::add(Num<T>::mul(dz, dz), l2)), T(0.5));
                                 };
                                 T h[16];
                                 h[0] = hsl(Num<T>::sub(c, z0), l2d);
-                                h[1] = hsl(Num<T>::sub(c, z1), l2s);
+                                h[1] = hsl(Num<T>::sub(z1, c), l2s);
                                 h[2] = hsl(Num<T>::sub(c, z2), l2d);
-                                h[3] = hsl(Num<T>::sub(c, z3), l2s);
+                                h[3] = hsl(Num<T>::sub(z3, c), l2s);
                                 h[4] = hsl(Num<T>::sub(c, z5), l2s);
                                 h[5] = hsl(Num<T>::sub(c, z6), l2d);
                                 h[6] = hsl(Num<T>::sub(c, z7), l2s);
                                 h[7] = hsl(Num<T>::sub(c, z8), l2d);
-                                h[8] = hsl(Num<T>::sub(z0, z1), l2e);
-                                h[9] = hsl(Num<T>::sub(z1, z2), l2e);
-                                h[10] = hsl(Num<T>::sub(z6, z7), l2e);
-                                h[11] = hsl(Num<T>::sub(z7, z8), l2e);
-                                h[12] = hsl(Num<T>::sub(z0, z3), l2e);
-                                h[13] = hsl(Num<T>::sub(z3, z6), l2e);
-                                h[14] = hsl(Num<T>::sub(z2, z5), l2e);
-                                h[15] = hsl(Num<T>::sub(z5, z8), l2e);
+                                h[8] = hsl(Num<T>::sub(z0, z1), l2s);
+                                h[9] = hsl(Num<T>::sub(z1, z2), l2s);
+                                h[10] = hsl(Num<T>::sub(z6, z7), l2s);
+                                h[11] = hsl(Num<T>::sub(z7, z8), l2s);
+                                h[12] = hsl(Num<T>::sub(z0, z3), l2s);
+                                h[13] = hsl(Num<T>::sub(z3, z6), l2s);
+                                h[14] = hsl(Num<T>::sub(z2, z5), l2s);
+                                h[15] = hsl(Num<T>::sub(z5, z8), l2s);
                                 auto heron = [](T a, T b, T cc3) {
                                     const T s2 = Num<T>::mul(Num<T>::add(Num<T>::add(a, b), cc3), T(0.5));
                                     T pr = Num<T>::mul(s2, Num<T>::sub(s2, a));
