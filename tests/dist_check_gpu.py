@@ -45,21 +45,45 @@ def main() -> None:
     x, y = lin % S, lin // S
     v = torch.randn(N, generator=g, device=dev)
     edges = np.linspace(0, 1.5 * S * 2.0, 31)[1:]
-    e, cnt, ssq = xs.pairwise_lag_binning(x, y, v, edges, 2.0)
+    e, cnt, ssq = xs.pairwise_lag_binning(x, y, v, edges, 2.0, distributed=True)
     assert int(cnt.sum()) == N * (N - 1) // 2
     # single-rank reference: temporarily pretend world == 1 by using a 1-rank subgroup
-    sub = None
-    for r in range(world):  # new_group is collective: every rank creates every 1-rank group
-        grp = dist.new_group([r])
-        if r == rank:
-            sub = grp
-    e1, cnt1, ssq1 = xs.pairwise_lag_binning(x, y, v, edges, 2.0, group=sub)
+    e1, cnt1, ssq1 = xs.pairwise_lag_binning(x, y, v, edges, 2.0)  # every rank alone on the full work list
     assert np.array_equal(cnt, cnt1) and np.allclose(ssq, ssq1, rtol=1e-9)
+    # Nuth-Kaab: row-sharded fit == single-GPU fit (identical radix-select medians; curve_fit sees the same 72 points)
+    from xdem_b200 import coreg
+
+    n = 512 * world
+    yy = torch.arange(n, device=dev, dtype=torch.float32)[:, None]
+    xx = torch.arange(768, device=dev, dtype=torch.float32)[None, :]
+
+    def surf(dx: float, dy: float) -> torch.Tensor:
+        return (1500 + 30 * torch.sin(0.05 * (xx + dx) + 0.02 * (yy + dy)) + 20 * torch.cos(0.031 * (yy + dy))
+                + 12 * torch.sin(0.09 * (xx + dx) - 0.07 * (yy + dy)))
+
+    ref = surf(0.0, 0.0)
+    tba = surf(0.37, -0.61) + 1.5
+    tba[300:303, 100:120] = float("nan")
+    tr = (5.0, 0, 0, 0, -5.0, 0)
+    single, n_single = coreg.nuth_kaab(ref, tba, transform=tr, tolerance=0.0, max_iterations=5,
+                                       params_random={"subsample": 1.0})
+    rows = n // world
+    shard, n_shard = xbd.sharded_nuth_kaab(ref[rank * rows:(rank + 1) * rows], tba[rank * rows:(rank + 1) * rows],
+                                           transform=tr, tolerance=0.0, max_iterations=5)
+    assert n_shard == n_single, (n_shard, n_single)
+    assert np.allclose(shard, single, rtol=1e-7, atol=1e-8), (shard, single)
+    assert abs(single[0] / 5 + 0.37) < 2e-2 and abs(single[1] / 5 + 0.61) < 2e-2, single
     dist.barrier()
     if rank == 0:
-        print(f"dist_check_gpu OK on {world} GPUs")
+        print(f"dist_check_gpu OK on {world} GPUs (terrain, variogram, Nuth-Kaab {shard})")
     dist.destroy_process_group()
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        import traceback
+
+        print(f"[rank {os.environ.get('RANK')}] FAILED:\n{traceback.format_exc()}", flush=True)
+        raise

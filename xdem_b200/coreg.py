@@ -53,21 +53,36 @@ def _u32_tensor(a: np.ndarray, dev: torch.device) -> torch.Tensor:
 class _NKState:
     """Device-resident state of one Nuth-Kaab fit (one GPU / one row shard)."""
 
-    def __init__(self, ref: torch.Tensor, tba: torch.Tensor, inlier_mask: torch.Tensor | None, group: Any = None):
+    def __init__(self, ref: torch.Tensor, tba: torch.Tensor, inlier_mask: torch.Tensor | None, group: Any = None,
+                 ref_halo: tuple[torch.Tensor | None, torch.Tensor | None] | None = None,
+                 tba_halo: tuple[torch.Tensor | None, torch.Tensor | None] | None = None):
+        """``ref`` / ``tba``: this GPU's rows.  Row-sharded fits (xdem_b200.distributed.sharded_nuth_kaab) pass the
+        neighbouring shards' rows: ``ref_halo`` = (1 row above, 1 row below) for np.gradient, ``tba_halo`` = (h rows
+        above, h rows below) for the shifted bilinear gather; None at a raster border.  With halos given, the
+        histogram / moment / range reductions are all-reduced over ``group``."""
         self.L = _lib.lib()
         self.dev = ref.device
-        self.ref = ref.contiguous()
-        self.tba = tba.contiguous()
         self.rows, self.cols = ref.shape
         self.group = group
+        self.sharded = ref_halo is not None or tba_halo is not None
         self.stream = ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
         n = self.rows * self.cols
+        rtop, rbot = ref_halo if ref_halo is not None else (None, None)
+        ttop, tbot = tba_halo if tba_halo is not None else (None, None)
+        ref_buf = torch.cat([t for t in (rtop, ref, rbot) if t is not None]).contiguous()
+        self._ref_buf = ref_buf
+        r0 = 0 if rtop is None else rtop.shape[0]
+        self.ref = ref_buf[r0:r0 + self.rows]
+        self.tba_buf = torch.cat([t for t in (ttop, tba, tbot) if t is not None]).contiguous()
+        self.tba_row0 = 0 if ttop is None else ttop.shape[0]
+        self.tba_halo_rows = (self.tba_row0, 0 if tbot is None else tbot.shape[0])
+        self.tba = self.tba_buf[self.tba_row0:self.tba_row0 + self.rows]
         self.slope_tan = torch.empty((self.rows, self.cols), dtype=torch.float32, device=self.dev)
         self.aspect = torch.empty_like(self.slope_tan)
         with torch.cuda.device(self.dev):
-            _lib.check(self.L.xb_nk_aux(self.ref.data_ptr(), self.rows, self.cols, self.ref.stride(0), 1, 1, 0,
-                                        self.rows, self.slope_tan.data_ptr(), self.aspect.data_ptr(), self.cols,
-                                        self.stream))
+            _lib.check(self.L.xb_nk_aux(ref_buf.data_ptr(), ref_buf.shape[0], self.cols, ref_buf.stride(0),
+                                        int(rtop is None), int(rbot is None), r0, r0 + self.rows,
+                                        self.slope_tan.data_ptr(), self.aspect.data_ptr(), self.cols, self.stream))
         # valid mask: inlier & finite(ref, tba, slope_tan, aspect)  (base.py:653-661)
         valid = torch.isfinite(self.ref) & torch.isfinite(self.tba) & torch.isfinite(self.slope_tan) \
             & torch.isfinite(self.aspect)
@@ -80,14 +95,29 @@ class _NKState:
 
     # ------------------------------------------------------------------ device passes
     def compute_dh(self, dx_px: float, dy_px: float) -> tuple[float, float, int]:
+        import torch.distributed as dist
+
+        if self.sharded:
+            need = int(np.ceil(abs(dy_px))) + 1
+            top, bot = self.tba_halo_rows
+            if (top and top < need) or (bot and bot < need):
+                raise ValueError(f"row shift of {dy_px:.2f} px exceeds the {min(top or bot, bot or top)}-row halo of the "
+                                 "sharded Nuth-Kaab fit; re-run with a larger `halo`")
         mm = _u32_tensor(np.array([0xFFFFFFFF, 0], dtype=np.uint32), self.dev)
         cnt = torch.zeros(1, dtype=torch.int64, device=self.dev)
         with torch.cuda.device(self.dev):
-            _lib.check(self.L.xb_nk_dh(self.ref.data_ptr(), self.tba.data_ptr(), self.sub_mask.data_ptr(),
+            _lib.check(self.L.xb_nk_dh(self.ref.data_ptr(), self.tba_buf.data_ptr(), self.sub_mask.data_ptr(),
                                        self.aspect.data_ptr(), self.rows, self.cols, self.ref.stride(0),
-                                       self.tba.stride(0), 0, self.rows, float(dx_px), float(dy_px),
-                                       self.dh.data_ptr(), mm.data_ptr(), cnt.data_ptr(), self.stream))
-        mmh = mm.cpu().numpy().view(np.uint32)
+                                       self.tba_buf.stride(0), self.tba_row0, self.tba_buf.shape[0], float(dx_px),
+                                       float(dy_px), self.dh.data_ptr(), mm.data_ptr(), cnt.data_ptr(), self.stream))
+        mm64 = mm.to(torch.int64) & 0xFFFFFFFF
+        if self.sharded and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            lo_t, hi_t = mm64[0:1].clone(), mm64[1:2].clone()
+            dist.all_reduce(lo_t, op=dist.ReduceOp.MIN, group=self.group)
+            dist.all_reduce(hi_t, op=dist.ReduceOp.MAX, group=self.group)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=self.group)
+            mm64 = torch.cat([lo_t, hi_t])
+        mmh = mm64.cpu().numpy().astype(np.uint32)
         n_fin = int(cnt.item())
         lo, hi = (float(v) for v in mmh.view(np.float32))
         return lo, hi, n_fin
@@ -95,7 +125,7 @@ class _NKState:
     def _allreduce(self, t: torch.Tensor, op: Any = None) -> None:
         import torch.distributed as dist
 
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+        if self.sharded and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(t, op=op or dist.ReduceOp.SUM, group=self.group)
 
     def _allreduce_min_u32(self, t_i32: torch.Tensor) -> np.ndarray:
@@ -103,7 +133,7 @@ class _NKState:
         import torch.distributed as dist
 
         v = t_i32.to(torch.int64) & 0xFFFFFFFF
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+        if self.sharded and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(v, op=dist.ReduceOp.MIN, group=self.group)
         return v.cpu().numpy().astype(np.uint32)
 
@@ -289,17 +319,24 @@ def nuth_kaab(ref_elev: Any, tba_elev: Any, inlier_mask: Any = None, transform: 
             m[idx_valid[pick]] = 1
             state.sub_mask = m.view(state.rows, state.cols).contiguous()
             n_valid = want
+    offsets = _iterate_nuth_kaab(state, transform, int(pf["bin_sizes"]), pf["fit_optimizer"], tolerance,
+                                 max_iterations)
+    return offsets, n_valid
+
+
+def _iterate_nuth_kaab(state: _NKState, transform: Any, bin_sizes: int, fit_optimizer: Callable[..., Any],
+                       tolerance: float, max_iterations: int) -> tuple[float, float, float]:
+    """`_iterate_method` (affine.py:102-147) around the GPU iteration step."""
     a_e = _transform_coeffs(transform)
     res = (abs(a_e[0]), abs(a_e[1]))
     offsets = (0.0, 0.0, 0.0)
-    for i in range(max_iterations):  # affine.py:102-147
-        offsets, stat = _nuth_kaab_iteration_step_gpu(offsets, state, res, a_e, int(pf["bin_sizes"]),
-                                                      pf["fit_optimizer"])
+    for i in range(max_iterations):
+        offsets, stat = _nuth_kaab_iteration_step_gpu(offsets, state, res, a_e, bin_sizes, fit_optimizer)
         logging.info("      Iteration #%d - Offset: %s; Magnitude: %s", i + 1, offsets, stat)
         if i > 1 and stat < tolerance:
             logging.info("   Last offset was below the residual offset threshold of %s -> stopping", tolerance)
             break
-    return offsets, n_valid
+    return offsets
 
 
 class NuthKaab:

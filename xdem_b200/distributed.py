@@ -85,3 +85,54 @@ def sharded_terrain_attribute(local_rows: torch.Tensor, resolution: float, surfa
     r0, r1, view = shard.prepare(buf, rows)
     return _engine.terrain_fused(view, resolution, surface_attributes, windowed_indexes, surface_fit=surface_fit,
                                  window_size=window_size, row_begin=r0, row_end=r1, **kwargs)
+
+
+def _exchange_rows(core: torch.Tensor, depth: int, rank: int, world: int, group: Any = None
+                   ) -> tuple[torch.Tensor | None, torch.Tensor | None]:
+    """(rows of the shard above, rows of the shard below) -- `depth` boundary rows from each neighbour, None at a raster
+    border."""
+    rows, cols = core.shape
+    buf = torch.empty((rows + 2 * depth, cols), dtype=core.dtype, device=core.device)
+    buf[depth:depth + rows] = core
+    RowShard(rank, world, depth, group).exchange(buf, rows)
+    top = buf[:depth].clone() if rank > 0 else None
+    bot = buf[rows + depth:].clone() if rank < world - 1 else None
+    return top, bot
+
+
+def sharded_nuth_kaab(ref_rows: torch.Tensor, tba_rows: torch.Tensor, inlier_rows: torch.Tensor | None = None,
+                      transform: Any = None, max_iterations: int = 10, tolerance: float = 0.001, bin_sizes: int = 72,
+                      halo: int = 16, group: Any = None) -> tuple[tuple[float, float, float], int]:
+    """Row-sharded Nuth & Kaab fit (BASELINE config 5): every rank passes its contiguous block of rows of the reference
+    and to-be-aligned DEMs (CUDA float32, rank order = north to south).  One halo row of the reference (np.gradient)
+    and `halo` rows of the to-be-aligned DEM (bilinear gather under the running shift; |row shift| must stay below
+    halo-1 pixels) are exchanged once over NCCL; per iteration only the radix-select histograms, the moments and the
+    aspect range are all-reduced (<= 72 x 256 x 8 B), and every rank runs the same 72-point curve_fit.  Returns the same
+    (easting, northing, vertical) offsets on every rank and the global number of valid pixels."""
+    import scipy.optimize
+
+    from . import coreg
+
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if ref_rows.shape != tba_rows.shape or ref_rows.dim() != 2:
+        raise ValueError("reference and to-be-aligned shards must be 2-D and of the same shape")
+    if world > 1 and ref_rows.shape[0] < halo:
+        raise ValueError(f"each shard needs at least {halo} rows")
+    ref_rows = ref_rows.to(torch.float32).contiguous()
+    tba_rows = tba_rows.to(torch.float32).contiguous()
+    if world > 1:
+        ref_halo = _exchange_rows(ref_rows, 1, rank, world, group)
+        tba_halo = _exchange_rows(tba_rows, halo, rank, world, group)
+    else:
+        ref_halo, tba_halo = (None, None), (None, None)
+    state = coreg._NKState(ref_rows, tba_rows, inlier_rows, group=group, ref_halo=ref_halo, tba_halo=tba_halo)
+    state.sharded = world > 1
+    n_valid = state.valid.sum().to(torch.int64).reshape(1)
+    if world > 1:
+        dist.all_reduce(n_valid, group=group)
+    if int(n_valid.item()) == 0:
+        raise ValueError("There is no valid points common to the input and auxiliary data.")
+    offsets = coreg._iterate_nuth_kaab(state, transform, int(bin_sizes), scipy.optimize.curve_fit, tolerance,
+                                       max_iterations)
+    return offsets, int(n_valid.item())

@@ -97,14 +97,16 @@ def _unit_prefix(n_groups: int) -> np.ndarray:
 
 def pairwise_lag_binning(x: torch.Tensor, y: torch.Tensor, v: torch.Tensor, edges: np.ndarray | None, gsd: float,
                          n_lags: int | None = None, maxlag: float | None = None, group: Any = None,
-                         estimator: str = "matheron") -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+                         estimator: str = "matheron", distributed: bool = False
+                         ) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
     """All-pairs lag binning of N grid samples (integer pixel coordinates x, y; float32 values v) on the GPU.
 
     ``edges`` = float64 right bin edges, or None for skgstat's "even" binning with ``n_lags`` classes over
     [0, min(maxlag, largest sampled distance)].  Returns (edges, count int64, third) where ``third`` is, per class,
     sum (v_i-v_j)^2 for "matheron", sum |v_i-v_j|^0.5 for "cressie", or the exact median of |v_i-v_j| for "dowd"
     (4 radix-select passes over all pairs).
-    If torch.distributed is initialised, the work units are split across ranks and count / sumsq all-reduced."""
+    With ``distributed=True`` (every rank of ``group`` calls with the SAME samples) the work units are split across
+    the ranks and the per-class results all-reduced (a few hundred bytes over NCCL)."""
     import torch.distributed as dist
 
     L = _lib.lib()
@@ -137,7 +139,7 @@ def pairwise_lag_binning(x: torch.Tensor, y: torch.Tensor, v: torch.Tensor, edge
         prefix = torch.from_numpy(prefix_np).to(dev)
         n_units = int(prefix_np[-1])
         rank, world = 0, 1
-        if dist.is_available() and dist.is_initialized():
+        if distributed and dist.is_available() and dist.is_initialized():
             rank, world = dist.get_rank(group), dist.get_world_size(group)
         u0 = n_units * rank // world
         u1 = n_units * (rank + 1) // world
