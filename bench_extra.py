@@ -22,13 +22,38 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+def _dist_setup():
+    """(rank, world, device); initialises NCCL when launched by torchrun."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(
+        os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    return rank, world, dev
+
+
+def _max_over_ranks(dt: float, dev) -> float:
+    import torch
+    import torch.distributed as dist
+
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return dt
+
+
 def bench_variogram(args) -> dict:
     import torch
 
     from oracle import c_oracle, variogram_oracle as vo
     from xdem_b200 import _lib, spatialstats as xs
 
-    dev = torch.device("cuda")
+    rank, world, dev = _dist_setup()
     S, gsd, n_lags = 32768, 5.0, 50
     g = torch.Generator(device=dev).manual_seed(44)
     lin = torch.randint(0, S * S, (int(args.n * 1.01),), generator=g, device=dev, dtype=torch.int64).unique()
@@ -43,12 +68,15 @@ def bench_variogram(args) -> dict:
         l0 = _lib.launch_count()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        edges, cnt, ssq = xs.pairwise_lag_binning(x, y, v, None, gsd, n_lags=n_lags, maxlag=maxlag)
+        edges, cnt, ssq = xs.pairwise_lag_binning(x, y, v, None, gsd, n_lags=n_lags, maxlag=maxlag,
+                                                  distributed=world > 1)
         torch.cuda.synchronize()
-        times.append(time.perf_counter() - t0)
+        times.append(_max_over_ranks(time.perf_counter() - t0, dev))
         launches = _lib.launch_count() - l0
     dt = min(times[1:])
     assert int(cnt.sum()) == pairs - 1  # every pair binned once; the farthest pair sits on the last (open) edge
+    if rank != 0:
+        return {}
     # CPU baseline: plain-C all-pairs binning (oracle), all threads, bounded N
     m = args.cpu_n
     xc = np.stack([(x[:m] * gsd).cpu().numpy().astype(np.float64), (y[:m] * gsd).cpu().numpy().astype(np.float64)], 1)
@@ -61,14 +89,14 @@ def bench_variogram(args) -> dict:
     issue_peak = sms * 4 * 32 * sm_clock  # thread-instructions / s
     return {
         "metric": "Gpairs/s all-pairs empirical variogram (Matheron, 50 even lag bins)", "value": pairs / dt / 1e9,
-        "unit": "Gpairs/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "dtype": "u32 distances / f32 diffs, u64 counts, f64 sums", "data": "synthetic",
+        "unit": "Gpairs/s", "n_gpus": world, "steps": args.steps, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "dtype": "u32 distances / f32 diffs, u64 counts, f64 sums", "data": "synthetic",
         "config": {"workload": f"sample_empirical_variogram core: {n} random samples of a 32768^2 grid, gsd 5, 50 even "
                                f"bins, includes Morton sort + max-distance pass + binning ({launches} kernel launches)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "issue (no HBM traffic: 16 MB of samples stay in L2)",
-                     "achieved": pairs / dt * 13 / 1e12, "peak": issue_peak / 1e12, "unit": "T thread-instr/s",
-                     "frac": pairs / dt * 13 / issue_peak,
+                     "achieved": pairs / dt * 13 / 1e12, "peak": world * issue_peak / 1e12, "unit": "T thread-instr/s",
+                     "frac": pairs / dt * 13 / (world * issue_peak),
                      "note": "13 issue slots per pair (DESIGN.md K2) x pairs/s vs 148 SM x 4 x 32 lanes x 1.965 GHz"},
         "cpu_baseline": {"value": m * (m - 1) / 2 / tc / 1e9, "unit": "Gpairs/s", "cores": c_oracle.num_threads(),
                          "kind": "port", "sample": f"first {m} of the same samples ({m*(m-1)//2:.3e} pairs, {tc:.1f} s)",
@@ -82,13 +110,15 @@ def bench_nuthkaab(args) -> dict:
     from oracle import nk_oracle
     from xdem_b200 import _lib, coreg
 
-    dev = torch.device("cuda")
+    rank, world, dev = _dist_setup()
     size = args.size
+    rows_local = size // world
+    row0 = rank * rows_local
 
     def surf(n, dx, dy, device):
-        yy = torch.arange(n, device=device, dtype=torch.float32)[:, None]
+        yy = (row0 + torch.arange(rows_local if n == size else n, device=device, dtype=torch.float32))[:, None]
         xx = torch.arange(n, device=device, dtype=torch.float32)[None, :]
-        z = torch.full((n, n), 1500.0, device=device)
+        z = torch.full((yy.shape[0], n), 1500.0, device=device)
         rng = np.random.default_rng(45)
         for _ in range(12):
             kx, ky = rng.uniform(0.01, 0.12, 2) * rng.choice([-1, 1], 2)
@@ -98,21 +128,29 @@ def bench_nuthkaab(args) -> dict:
 
     g = torch.Generator(device=dev).manual_seed(46)
     ref = surf(size, 0.0, 0.0, dev)
-    tba = surf(size, 0.37, -0.61, dev) + 1.5 + 0.01 * torch.randn((size, size), generator=g, device=dev)
+    tba = surf(size, 0.37, -0.61, dev) + 1.5 + 0.01 * torch.randn(tuple(ref.shape), generator=g, device=dev)
     times = []
     for rep in range(args.steps + 1):
         l0 = _lib.launch_count()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        (e, n, vz), used = coreg.nuth_kaab(ref, tba, transform=(5.0, 0, 0, 0, -5.0, 0), tolerance=0.0,
-                                           max_iterations=10, params_random={"subsample": 1.0})
+        if world > 1:
+            from xdem_b200 import distributed as xbd
+
+            (e, n, vz), used = xbd.sharded_nuth_kaab(ref, tba, transform=(5.0, 0, 0, 0, -5.0, 0), tolerance=0.0,
+                                                     max_iterations=10)
+        else:
+            (e, n, vz), used = coreg.nuth_kaab(ref, tba, transform=(5.0, 0, 0, 0, -5.0, 0), tolerance=0.0,
+                                               max_iterations=10, params_random={"subsample": 1.0})
         torch.cuda.synchronize()
-        times.append(time.perf_counter() - t0)
+        times.append(_max_over_ranks(time.perf_counter() - t0, dev))
         launches = _lib.launch_count() - l0
     dt = min(times[1:])
     assert abs(e / 5 + 0.37) < 2e-3 and abs(n / 5 + 0.61) < 2e-3 and abs(vz + 1.5) < 2e-3, (e, n, vz)
+    if rank != 0:
+        return {}
     # CPU baseline: NumPy/SciPy restatement of the reference's iteration (same code path as xdem on a CPU)
-    cs = args.cpu_size
+    cs = min(args.cpu_size, rows_local)
     rc, tc_ = ref[:cs, :cs].cpu().numpy(), tba[:cs, :cs].cpu().numpy()
     t0 = time.perf_counter()
     nk_oracle.nuth_kaab(rc, tc_, None, (5.0, -5.0), 0.0, 10)
@@ -125,14 +163,15 @@ def bench_nuthkaab(args) -> dict:
     algo = (12 + 10 * 16) * size * size  # aux once + 16 B/px/iteration
     return {
         "metric": "Mpixel*iteration/s Nuth-Kaab (dense, 10 iterations)", "value": size * size * 10 / dt / 1e6,
-        "unit": "Mpixel*iter/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "unit": "Mpixel*iter/s", "n_gpus": world, "steps": args.steps, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "strong",
         "dtype": "f32 rasters, f64 interpolation/moments, exact medians", "data": "synthetic",
         "config": {"workload": f"NuthKaab {size}^2 ref/tba pair, subsample=1, 10 iterations, 72 aspect bins, host "
                                f"curve_fit ({launches} kernel launches); recovered shift px "
                                f"({-e/5:.4f}, {-n/5:.4f}), dz {vz:.4f}"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": algo / dt / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": algo / dt / 1e9 / peak,
+        "roofline": {"bound": "hbm", "achieved": algo / dt / 1e9, "peak": peak * world, "unit": "GB/s",
+                     "frac": algo / dt / 1e9 / (peak * world),
                      "note": "algorithmic minimum 12 B/px (aux) + 16 B/px/iteration; the radix-select medians stream "
                              "~7 passes per iteration (DESIGN.md K3)"},
         "cpu_baseline": {"value": cs * cs * 10 / tcpu / 1e6, "unit": "Mpixel*iter/s", "cores": 1, "kind": "port",
@@ -152,7 +191,13 @@ def main() -> None:
     ap.add_argument("--cpu-size", type=int, default=1024)
     args = ap.parse_args()
     line = bench_variogram(args) if args.workload == "variogram" else bench_nuthkaab(args)
-    print(json.dumps(line), flush=True)
+    if line:
+        print(json.dumps(line), flush=True)
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
