@@ -227,7 +227,6 @@ def main() -> None:
         return
 
     # ------------------------------------------------------------------ CUDA arm ----------------------------------
-    import numpy as np
     import torch
     import torch.distributed as dist
 

@@ -50,7 +50,7 @@ def _max_over_ranks(dt: float, dev) -> float:
 def bench_variogram(args) -> dict:
     import torch
 
-    from oracle import c_oracle, variogram_oracle as vo
+    from oracle import c_oracle
     from xdem_b200 import _lib, spatialstats as xs
 
     rank, world, dev = _dist_setup()

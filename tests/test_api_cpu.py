@@ -106,3 +106,48 @@ def test_product_never_imports_oracle() -> None:
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+
+
+def test_install_rebinds_reference_seam(monkeypatch) -> None:
+    """xdem_b200.install() replaces the two seam names inside an importable `xdem.terrain.terrain` (SURVEY 8b mode ii)."""
+    import sys
+    import types
+
+    import xdem_b200
+    from xdem_b200.surfit import _get_surface_attributes
+    from xdem_b200.window import _get_windowed_indexes
+
+    fake_xdem, fake_terrain_pkg = types.ModuleType("xdem"), types.ModuleType("xdem.terrain")
+    fake_mod = types.ModuleType("xdem.terrain.terrain")
+    fake_mod._get_surface_attributes = lambda *a, **k: "cpu"
+    fake_mod._get_windowed_indexes = lambda *a, **k: "cpu"
+    fake_xdem.terrain, fake_terrain_pkg.terrain = fake_terrain_pkg, fake_mod
+    monkeypatch.setitem(sys.modules, "xdem", fake_xdem)
+    monkeypatch.setitem(sys.modules, "xdem.terrain", fake_terrain_pkg)
+    monkeypatch.setitem(sys.modules, "xdem.terrain.terrain", fake_mod)
+    xdem_b200.install()
+    assert fake_mod._get_surface_attributes is _get_surface_attributes
+    assert fake_mod._get_windowed_indexes is _get_windowed_indexes
+
+
+def test_variogram_and_coreg_validation_without_gpu() -> None:
+    """spatialstats.py:1376-1393 messages and the NuthKaab constructor checks (affine.py:68-100) are raised on the host."""
+    from xdem_b200 import coreg
+    from xdem_b200 import spatialstats as xs
+
+    v2 = np.zeros((8, 8), dtype=np.float32)
+    with pytest.raises(ValueError, match="ground sampling distance must be defined"):
+        xs.sample_empirical_variogram(v2, subsample=10, subsample_method="pdist_point")
+    with pytest.raises(ValueError, match="Values array must be 2D"):
+        xs.sample_empirical_variogram(v2.ravel(), gsd=1.0, subsample=10, subsample_method="pdist_point")
+    with pytest.raises(TypeError, match="subsampling method must be one of"):
+        xs.sample_empirical_variogram(v2, gsd=1.0, subsample_method="nope")
+    with pytest.raises(NotImplementedError):
+        xs.sample_empirical_variogram(v2, gsd=1.0)  # default scikit-gstat equidistant sampler
+    with pytest.raises(TypeError, match="`fit_optimizer` must be a function"):
+        coreg.NuthKaab(fit_optimizer=3)  # type: ignore
+    with pytest.raises(TypeError, match="`bin_sizes` must be an integer"):
+        coreg.NuthKaab(bin_sizes=2.5)  # type: ignore
+    nk = coreg.NuthKaab()
+    assert nk.meta["inputs"]["iterative"] == {"max_iterations": 10, "tolerance": 0.001}
+    assert nk.meta["inputs"]["random"]["subsample"] == 5e5 and nk.meta["inputs"]["fitorbin"]["bin_sizes"] == 72

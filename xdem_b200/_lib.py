@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p
+from ctypes import c_char_p, c_double, c_int, c_int64, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libxdem_b200.so")
@@ -100,4 +100,4 @@ EXPORTED = ["xb_last_error", "xb_version", "xb_launch_count", "xb_terrain_fused"
             "xb_nk_dh", "xb_nk_hist", "xb_nk_next", "xb_nk_make_keys", "xb_nk_hist_keys", "xb_nk_next_keys",
             "xb_windowed_generic", "xb_set_option", "xb_shift_resample"]
 
-__all__ = ["lib", "check", "launch_count", "XdemB200Error", "LIB_PATH", "EXPORTED", "c_int32"]
+__all__ = ["lib", "check", "launch_count", "set_option", "XdemB200Error", "LIB_PATH", "EXPORTED"]

@@ -130,13 +130,11 @@ int xb_build_terrain_params(xbt::TerrainParams& p, int dtype, double resolution,
         const float diag = (float)sqrt(2.0) * L;
         p.rug_dl2_diag = (double)(diag * diag);
         p.rug_dl2_straight = (double)(L * L);
-        p.rug_dl2_edge = (double)(L * L);
         p.rug_ll = (double)(float)(r * r);
     } else {
         const double diag = sqrt(2.0) * r;
         p.rug_dl2_diag = diag * diag;
         p.rug_dl2_straight = r * r;
-        p.rug_dl2_edge = r * r;
         p.rug_ll = r * r;
     }
     *hs_out = hs;

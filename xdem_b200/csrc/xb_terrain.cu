@@ -505,8 +505,6 @@ static int launch_halo_sel(int hs, int hw, bool use_tma, const CUtensorMap& tmap
     return XB_ERR_UNSUPPORTED;
 }
 
-int tile_rows(int) { return NWARPS * 8; }
-
 int launch(const TerrainParams& p_in, int dtype, int hs, int hw, cudaStream_t stream) {
     TerrainParams p = p_in;
     const int H = hs > hw ? hs : hw;

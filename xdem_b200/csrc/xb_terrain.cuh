@@ -27,12 +27,11 @@ struct TerrainParams {
     double inv_d1, inv_d2, inv_d3;  // 1/divider of (z_x,z_y), (z_xx,z_yy), z_xy  (surfit.py:278-304)
     double rad2deg;
     double hs_sin_alt, hs_kx, hs_ky, zf2;  // hillshade constants (surfit.py:606-622)
-    double rug_dl2_diag, rug_dl2_straight, rug_dl2_edge, rug_ll;  // rugosity constants in the DEM dtype
+    double rug_dl2_diag, rug_dl2_straight, rug_ll;  // rugosity constants in the DEM dtype (window.py:628-651)
 };
 
 int launch(const TerrainParams& p, int dtype, int hs, int hw, cudaStream_t stream);
 // float32 Florinsky surface attributes with row-feature reuse (xb_terrain_fl.cu); needs a TMA-eligible raster
 int launch_florinsky_sliding(const TerrainParams& p, cudaStream_t stream);
-int tile_rows(int halo);
 
 }  // namespace xbt

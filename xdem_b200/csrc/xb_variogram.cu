@@ -31,10 +31,6 @@ constexpr int NWARPS = 8;
 constexpr int NTHREADS = NWARPS * 32;
 constexpr int CHUNK_J = 32;  // j-groups per work unit
 
-struct Box {
-    int x0, y0, x1, y1;
-};
-
 __device__ __forceinline__ void box_dist2(const int4& a, const int4& b, unsigned long long& dmin2,
                                           unsigned long long& dmax2) {
     const long long dxmin = max(0, max(a.x - b.z, b.x - a.z));
