@@ -60,10 +60,14 @@ __device__ __forceinline__ void store2(void* plane, long long off, bool full, in
 }
 
 // rows r = -2..2 of the current output row are ring slots S0..S4
-template <bool ALG>
+// CMASK != 0: the surface-attribute mask is a compile-time constant (common requests), which turns the attribute blocks
+// into one straight-line region the scheduler can interleave; CMASK == 0: runtime mask.
+template <bool ALG, unsigned CMASK>
 __device__ __forceinline__ void emit_row(const RowFeat& r0, const RowFeat& r1, const RowFeat& r2, const RowFeat& r3,
-                                         const RowFeat& r4, const TerrainParams& p, long long off, bool full, int nvalid,
-                                         bool need2, bool need_sah) {
+                                         const RowFeat& r4, const TerrainParams& p, long long off, bool full, int nvalid) {
+    const unsigned mask = CMASK ? CMASK : p.surf_mask;
+    const bool need2 = (mask & ~7u) != 0;
+    const bool need_sah = (mask & 7u) != 0;
     float sx[2], sy[2], sxx[2], syy[2], sxy[2], car[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -106,12 +110,12 @@ __device__ __forceinline__ void emit_row(const RowFeat& r0, const RowFeat& r1, c
             g2[k] = fmaf(zx[k], zx[k], zy[k] * zy[k]);
         }
         const float ang = p.degrees ? (float)p.rad2deg : 1.0f;
-        if (p.surf_mask & 1u)
+        if (mask & 1u)
             store2(p.out[0], off, full, nvalid, slope_rad(g2[0]) * ang + car[0], slope_rad(g2[1]) * ang + car[1]);
-        if (p.surf_mask & 2u)
+        if (mask & 2u)
             store2(p.out[1], off, full, nvalid, aspect_rad(zx[0], zy[0]) * ang + car[0],
                    aspect_rad(zx[1], zy[1]) * ang + car[1]);
-        if (p.surf_mask & 4u) {
+        if (mask & 4u) {
             const float ky = (float)p.hs_ky, kx = -(float)p.hs_kx, sa = (float)p.hs_sin_alt, zf2 = (float)p.zf2;
             const float lo = p.clip_hs ? 0.0f : -CUDART_INF_F, hi = p.clip_hs ? 255.0f : CUDART_INF_F;
             float o[2];
@@ -124,25 +128,25 @@ __device__ __forceinline__ void emit_row(const RowFeat& r0, const RowFeat& r1, c
             store2(p.out[2], off, full, nvalid, o[0], o[1]);
         }
     }
-    if (p.surf_mask & 8u) {
+    if (mask & 8u) {
         const float f = (float)(-200.0 * p.inv_d2);
         store2(p.out[3], off, full, nvalid, (sxx[0] + syy[0]) * f + car[0], (sxx[1] + syy[1]) * f + car[1]);
     }
     if constexpr (ALG) {
-        if (p.surf_mask & ~15u) {
+        if (mask & ~15u) {
             float r6a[6], r6b[6];
             curv_alg<float>(sx[0], sy[0], sxx[0], syy[0], sxy[0], p, r6a);
             curv_alg<float>(sx[1], sy[1], sxx[1], syy[1], sxy[1], p, r6b);
 #pragma unroll
             for (int a = 0; a < 6; ++a)
-                if (p.surf_mask & (1u << (4 + a)))
+                if (mask & (1u << (4 + a)))
                     store2(p.out[4 + a], off, full, nvalid, r6a[a] + car[0], r6b[a] + car[1]);
         }
     }
 }
 
-template <bool ALG, int OCC>
-__global__ void __launch_bounds__(NTHREADS, OCC)
+template <bool ALG, unsigned CMASK>
+__global__ void __launch_bounds__(NTHREADS, 2)
 florinsky_sliding_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TerrainParams p) {
     constexpr uint32_t STAGE_BYTES = BOXW * FL_BOXH * sizeof(float);
     constexpr int STAGE_ELEMS = ((STAGE_BYTES + 127) / 128) * 128 / sizeof(float);
@@ -173,8 +177,6 @@ florinsky_sliding_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
             }
         }
     }
-    const bool need2 = (p.surf_mask & ~7u) != 0;
-    const bool need_sah = (p.surf_mask & 7u) != 0;
     const bool vec_ok = p.vec_ok != 0;
 
     int it = 0;
@@ -206,7 +208,7 @@ florinsky_sliding_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
                 // five output rows per trip: the ring returns to its starting assignment
 #define XB_FL_STEP(NEW, A, B, C, D, E)                                                   \
     make_features(rp, NEW);                                                              \
-    if (y < p.row_end) emit_row<ALG>(A, B, C, D, E, p, off, full, nvalid, need2, need_sah); \
+    if (y < p.row_end) emit_row<ALG, CMASK>(A, B, C, D, E, p, off, full, nvalid);              \
     rp += BOXW, off += p.out_ld, ++y;
                 XB_FL_STEP(f4, f0, f1, f2, f3, f4)
                 XB_FL_STEP(f0, f1, f2, f3, f4, f0)
@@ -270,9 +272,12 @@ int launch_florinsky_sliding(const TerrainParams& p_in, cudaStream_t stream) {
         XB_CUDA_CHECK(cudaGetLastError());
         return XB_OK;
     };
-    // 2 CTAs/SM: the 5-row feature ring needs ~100 registers (a 3-CTA build spills and measured 40 % slower)
-    if (alg) return launch_one(florinsky_sliding_kernel<true, 2>);
-    return launch_one(florinsky_sliding_kernel<false, 2>);
+    // 2 CTAs/SM: the 5-row feature ring needs ~100 registers (a 3-CTA build spills and measured 40 % slower).
+    // The two headline requests get compile-time attribute masks.
+    if (alg) return launch_one(florinsky_sliding_kernel<true, 0u>);
+    if (p.surf_mask == 15u) return launch_one(florinsky_sliding_kernel<false, 15u>);  // slope+aspect+hillshade+curvature
+    if (p.surf_mask == 11u) return launch_one(florinsky_sliding_kernel<false, 11u>);  // slope+aspect+curvature
+    return launch_one(florinsky_sliding_kernel<false, 0u>);
 }
 
 }  // namespace xbt
