@@ -49,9 +49,10 @@ __device__ __forceinline__ void make_features(const float* row, RowFeat& f) {
     }
 }
 
+template <bool FAST>
 __device__ __forceinline__ void store2(void* plane, long long off, bool full, int nvalid, float v0, float v1) {
     float* p = reinterpret_cast<float*>(plane) + off;
-    if (full) {
+    if (FAST || full) {
         __stcs(reinterpret_cast<float2*>(p), make_float2(v0, v1));
     } else {
         if (nvalid > 0) __stcs(p, v0);
@@ -62,7 +63,8 @@ __device__ __forceinline__ void store2(void* plane, long long off, bool full, in
 // rows r = -2..2 of the current output row are ring slots S0..S4
 // CMASK != 0: the surface-attribute mask is a compile-time constant (common requests), which turns the attribute blocks
 // into one straight-line region the scheduler can interleave; CMASK == 0: runtime mask.
-template <bool ALG, unsigned CMASK>
+// FAST: the whole warp strip is inside the raster and 8-byte aligned -> unconditional vector stores, no row test.
+template <bool ALG, unsigned CMASK, bool FAST>
 __device__ __forceinline__ void emit_row(const RowFeat& r0, const RowFeat& r1, const RowFeat& r2, const RowFeat& r3,
                                          const RowFeat& r4, const TerrainParams& p, long long off, bool full, int nvalid) {
     const unsigned mask = CMASK ? CMASK : p.surf_mask;
@@ -111,9 +113,9 @@ __device__ __forceinline__ void emit_row(const RowFeat& r0, const RowFeat& r1, c
         }
         const float ang = p.degrees ? (float)p.rad2deg : 1.0f;
         if (mask & 1u)
-            store2(p.out[0], off, full, nvalid, slope_rad(g2[0]) * ang + car[0], slope_rad(g2[1]) * ang + car[1]);
+            store2<FAST>(p.out[0], off, full, nvalid, slope_rad(g2[0]) * ang + car[0], slope_rad(g2[1]) * ang + car[1]);
         if (mask & 2u)
-            store2(p.out[1], off, full, nvalid, aspect_rad(zx[0], zy[0]) * ang + car[0],
+            store2<FAST>(p.out[1], off, full, nvalid, aspect_rad(zx[0], zy[0]) * ang + car[0],
                    aspect_rad(zx[1], zy[1]) * ang + car[1]);
         if (mask & 4u) {
             const float ky = (float)p.hs_ky, kx = -(float)p.hs_kx, sa = (float)p.hs_sin_alt, zf2 = (float)p.zf2;
@@ -125,12 +127,12 @@ __device__ __forceinline__ void emit_row(const RowFeat& r0, const RowFeat& r1, c
                 const float inner = fmaf(ky, zy[k], fmaf(kx, zx[k], sa));
                 o[k] = fminf(fmaxf(fmaf(254.0f * r, inner, 1.5f), lo), hi) + car[k];
             }
-            store2(p.out[2], off, full, nvalid, o[0], o[1]);
+            store2<FAST>(p.out[2], off, full, nvalid, o[0], o[1]);
         }
     }
     if (mask & 8u) {
         const float f = (float)(-200.0 * p.inv_d2);
-        store2(p.out[3], off, full, nvalid, (sxx[0] + syy[0]) * f + car[0], (sxx[1] + syy[1]) * f + car[1]);
+        store2<FAST>(p.out[3], off, full, nvalid, (sxx[0] + syy[0]) * f + car[0], (sxx[1] + syy[1]) * f + car[1]);
     }
     if constexpr (ALG) {
         if (mask & ~15u) {
@@ -140,7 +142,7 @@ __device__ __forceinline__ void emit_row(const RowFeat& r0, const RowFeat& r1, c
 #pragma unroll
             for (int a = 0; a < 6; ++a)
                 if (mask & (1u << (4 + a)))
-                    store2(p.out[4 + a], off, full, nvalid, r6a[a] + car[0], r6b[a] + car[1]);
+                    store2<FAST>(p.out[4 + a], off, full, nvalid, r6a[a] + car[0], r6b[a] + car[1]);
         }
     }
 }
@@ -194,6 +196,8 @@ florinsky_sliding_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
         // first staged row of this warp = tile row wy*15 (i.e. output row - 2); column x0 - 2
         const float* base = tile + (size_t)(wy * FL_RPW) * BOXW + (XOFF + wx * 64 + 2 * lane - 2);
         const long long y_first = y_tile + wy * FL_RPW;
+        // interior strips (all 32 lanes write two pixels, all 15 rows exist) take the branch-free path
+        const bool warp_fast = __all_sync(0xffffffffu, full) && (y_first + FL_RPW <= p.row_end);
         if (active && y_first < p.row_end) {
             RowFeat f0, f1, f2, f3, f4;
             make_features(base + 0 * BOXW, f0);
@@ -201,22 +205,38 @@ florinsky_sliding_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
             make_features(base + 2 * BOXW, f2);
             make_features(base + 3 * BOXW, f3);
             long long off = (y_first - p.row_begin) * p.out_ld + x0;
-            long long y = y_first;
+            // five output rows per trip: the ring returns to its starting assignment
+#define XB_FL_RING(STEP)               \
+    STEP(f4, f0, f1, f2, f3, f4)       \
+    STEP(f0, f1, f2, f3, f4, f0)       \
+    STEP(f1, f2, f3, f4, f0, f1)       \
+    STEP(f2, f3, f4, f0, f1, f2)       \
+    STEP(f3, f4, f0, f1, f2, f3)
+            if (warp_fast) {
 #pragma unroll 1
-            for (int g = 0; g < FL_RPW / 5; ++g) {
-                const float* rp = base + (size_t)(4 + 5 * g) * BOXW;
-                // five output rows per trip: the ring returns to its starting assignment
-#define XB_FL_STEP(NEW, A, B, C, D, E)                                                   \
-    make_features(rp, NEW);                                                              \
-    if (y < p.row_end) emit_row<ALG, CMASK>(A, B, C, D, E, p, off, full, nvalid);              \
-    rp += BOXW, off += p.out_ld, ++y;
-                XB_FL_STEP(f4, f0, f1, f2, f3, f4)
-                XB_FL_STEP(f0, f1, f2, f3, f4, f0)
-                XB_FL_STEP(f1, f2, f3, f4, f0, f1)
-                XB_FL_STEP(f2, f3, f4, f0, f1, f2)
-                XB_FL_STEP(f3, f4, f0, f1, f2, f3)
+                for (int g = 0; g < FL_RPW / 5; ++g) {
+                    const float* rp = base + (size_t)(4 + 5 * g) * BOXW;
+#define XB_FL_STEP(NEW, A, B, C, D, E)                                   \
+    make_features(rp, NEW);                                              \
+    emit_row<ALG, CMASK, true>(A, B, C, D, E, p, off, true, 2);          \
+    rp += BOXW, off += p.out_ld;
+                    XB_FL_RING(XB_FL_STEP)
 #undef XB_FL_STEP
+                }
+            } else {
+                long long y = y_first;
+#pragma unroll 1
+                for (int g = 0; g < FL_RPW / 5; ++g) {
+                    const float* rp = base + (size_t)(4 + 5 * g) * BOXW;
+#define XB_FL_STEP(NEW, A, B, C, D, E)                                                            \
+    make_features(rp, NEW);                                                                       \
+    if (y < p.row_end) emit_row<ALG, CMASK, false>(A, B, C, D, E, p, off, full, nvalid);          \
+    rp += BOXW, off += p.out_ld, ++y;
+                    XB_FL_RING(XB_FL_STEP)
+#undef XB_FL_STEP
+                }
             }
+#undef XB_FL_RING
         }
         __syncthreads();
         if (tid == 0) {

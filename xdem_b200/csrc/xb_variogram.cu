@@ -326,18 +326,21 @@ variogram_maxd2_kernel(const int4* __restrict__ pts, const int4* __restrict__ gb
     }
 }
 
-static unsigned long long* g_counter = nullptr;
-static int g_counter_dev = -1;
-
-static int ensure_counter() {
-    int dev = 0;
-    XB_CUDA_CHECK(cudaGetDevice(&dev));
-    if (!g_counter || g_counter_dev != dev) {
-        XB_CUDA_CHECK(cudaMalloc(&g_counter, 2 * sizeof(unsigned long long)));
-        g_counter_dev = dev;
+// Work counter of one launch: allocated from the stream-ordered pool (cudaMallocAsync) so that concurrent calls on
+// different streams / threads never share state.
+struct WorkCounter {
+    unsigned long long* ptr = nullptr;
+    cudaStream_t st = nullptr;
+    int init(cudaStream_t s) {
+        st = s;
+        XB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&ptr), sizeof(unsigned long long), st));
+        XB_CUDA_CHECK(cudaMemsetAsync(ptr, 0, sizeof(unsigned long long), st));
+        return XB_OK;
     }
-    return XB_OK;
-}
+    ~WorkCounter() {
+        if (ptr) cudaFreeAsync(ptr, st);
+    }
+};
 
 }  // namespace xbv
 
@@ -357,10 +360,10 @@ int xb_variogram_pairs(const int32_t* pts_dev, const int32_t* gbox_dev, int64_t 
         return XB_ERR_INVALID;
     }
     if (unit_end <= unit_begin) return XB_OK;
-    int rc = xbv::ensure_counter();
-    if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    XB_CUDA_CHECK(cudaMemsetAsync(xbv::g_counter, 0, sizeof(unsigned long long), st));
+    xbv::WorkCounter wc;
+    int rc = wc.init(st);
+    if (rc) return rc;
     int num_sms = 0;
     rc = xb_num_sms(&num_sms);
     if (rc) return rc;
@@ -376,7 +379,7 @@ int xb_variogram_pairs(const int32_t* pts_dev, const int32_t* gbox_dev, int64_t 
     }
 #define XB_VG_LAUNCH(D2T, EST)                                                                                     \
     xbv::variogram_pairs_kernel<D2T, EST><<<(unsigned)grid, xbv::NTHREADS, 0, st>>>(                                \
-        pts, gbox, (int)n_groups, edge2_dev, n_bins, pref, unit_begin, unit_end, xbv::g_counter, count_dev, sumsq_dev)
+        pts, gbox, (int)n_groups, edge2_dev, n_bins, pref, unit_begin, unit_end, wc.ptr, count_dev, sumsq_dev)
     if (wide) {
         if (estimator) XB_VG_LAUNCH(unsigned long long, 1); else XB_VG_LAUNCH(unsigned long long, 0);
     } else {
@@ -404,10 +407,10 @@ int xb_variogram_median_pass(const int32_t* pts_dev, const int32_t* gbox_dev, in
         return XB_ERR_UNSUPPORTED;
     }
     if (unit_end <= unit_begin) return XB_OK;
-    int rc = xbv::ensure_counter();
-    if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    XB_CUDA_CHECK(cudaMemsetAsync(xbv::g_counter, 0, sizeof(unsigned long long), st));
+    xbv::WorkCounter wc;
+    int rc = wc.init(st);
+    if (rc) return rc;
     int num_sms = 0;
     rc = xb_num_sms(&num_sms);
     if (rc) return rc;
@@ -421,7 +424,7 @@ int xb_variogram_median_pass(const int32_t* pts_dev, const int32_t* gbox_dev, in
     auto launch = [&](auto kern) -> int {
         XB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)grid, xbv::NTHREADS, smem, st>>>(pts, gbox, (int)n_groups, edge2_dev, n_bins, pref, unit_begin,
-                                                          unit_end, xbv::g_counter, prefix_dev, prefix_mask, shift,
+                                                          unit_end, wc.ptr, prefix_dev, prefix_mask, shift,
                                                           hist_dev, next_key_dev);
         XB_CUDA_CHECK(cudaGetLastError());
         return XB_OK;
@@ -439,17 +442,17 @@ int xb_variogram_maxd2(const int32_t* pts_dev, const int32_t* gbox_dev, int64_t 
         xb_set_error("bad arguments to xb_variogram_maxd2");
         return XB_ERR_INVALID;
     }
-    int rc = xbv::ensure_counter();
-    if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    XB_CUDA_CHECK(cudaMemsetAsync(xbv::g_counter, 0, sizeof(unsigned long long), st));
+    xbv::WorkCounter wc;
+    int rc = wc.init(st);
+    if (rc) return rc;
     int num_sms = 0;
     rc = xb_num_sms(&num_sms);
     if (rc) return rc;
     long long grid = std::min<long long>((long long)num_sms * 2, (n_groups + xbv::NWARPS - 1) / xbv::NWARPS);
     xbv::variogram_maxd2_kernel<<<(unsigned)grid, xbv::NTHREADS, 0, st>>>(
         reinterpret_cast<const int4*>(pts_dev), reinterpret_cast<const int4*>(gbox_dev), (int)n_groups,
-        xbv::g_counter, maxd2_dev);
+        wc.ptr, maxd2_dev);
     XB_CUDA_CHECK(cudaGetLastError());
     xb_count_launch(1);
     return XB_OK;
