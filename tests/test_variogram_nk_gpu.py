@@ -162,6 +162,32 @@ def test_nk_step_pieces_vs_oracle() -> None:
         assert s1 / n == pytest.approx(dbg["p0"][2], rel=1e-3, abs=1e-3)
 
 
+@pytest.mark.parametrize("ncols", [299, 296, 5, 4])
+def test_nk_dh_vector_and_scalar_kernels(ncols: int) -> None:
+    """xb_nk_dh picks a 4-pixels-per-thread kernel for 16-byte aligned rasters and a scalar one otherwise: both against
+    the oracle, including shifts whose 2x2 stencils cross the raster border."""
+    import torch
+
+    from oracle import nk_oracle as nk
+    from xdem_b200 import coreg
+
+    g = parity.load_golden("nk_reference.npz")
+    ref, tba, inl = (np.ascontiguousarray(g[k][:, :ncols]) for k in ("ref", "tba", "inlier"))
+    slope_tan, aspect = nk.aux_vars(ref)
+    valid = np.isfinite(ref) & np.isfinite(tba) & np.isfinite(slope_tan) & np.isfinite(aspect) & inl
+    st = coreg._NKState(torch.from_numpy(ref).cuda(), torch.from_numpy(tba).cuda(), torch.from_numpy(inl).cuda())
+    for dx, dy in ((0.0, 0.0), (0.37, -0.61), (-1.46, 2.58), (3.0, -2.0), (-4.75, 0.5)):
+        _, _, n_fin = st.compute_dh(dx, dy)
+        dh_o = nk.dh_at(ref, tba, valid, dx, dy)
+        dh_g = st.dh.cpu().numpy().reshape(ref.shape)[valid]
+        assert np.array_equal(np.isnan(dh_g), np.isnan(dh_o)), (ncols, dx, dy)
+        assert n_fin == int(np.isfinite(dh_o).sum())
+        m = np.isfinite(dh_o)
+        assert np.allclose(dh_g[m], dh_o[m], rtol=0, atol=2e-4)
+        # everything outside the subsample stays NaN
+        assert np.isnan(st.dh.cpu().numpy().reshape(ref.shape)[~valid]).all()
+
+
 def test_nk_full_fit_vs_reference_fixture() -> None:
     """Whole fit against the per-iteration outputs of the reference's own code (tests/golden/nk_reference.npz)."""
     from xdem_b200 import coreg
