@@ -56,7 +56,8 @@ int xb_version(void);
 /* Number of kernels this library launched since load (all entry points); bench.py reports it as gpu_launches. */
 uint64_t xb_launch_count(void);
 /* Tuning / test knobs.  "florinsky_generic" = 1 routes Florinsky requests through the generic fused kernel instead of
- * the row-feature-reuse kernel (both are parity-tested; used for A/B checks). */
+ * the row-feature-reuse kernel (both are parity-tested; used for A/B checks).  "variogram_full_tiles" = bit mask (default
+ * 7): bit k-1 lets interior variogram tiles that span exactly k lag classes use the threshold-light sweep. */
 int xb_set_option(const char* name, int value);
 
 /* ---------------------------------------------------------------------------------------------------------------

@@ -87,3 +87,4 @@ typedef CUresult (*xb_cuTensorMapEncodeTiled_t)(CUtensorMap*, CUtensorMapDataTyp
 xb_cuTensorMapEncodeTiled_t xb_get_tensormap_encoder();
 int xb_num_sms(int* out);
 bool xb_option_florinsky_generic();
+int xb_option_variogram_full_tiles();  // bit k-1: interior tiles spanning k lag classes take the threshold-light sweep
