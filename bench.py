@@ -352,7 +352,9 @@ def main() -> None:
             "vs_baseline": None, "dtype": "f32 (exact-difference fp32 stencils; fp64 curvature algebra)",
             "data": "synthetic", "config": config, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "xbt::terrain_fused_kernel",
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": ("xbt::florinsky_sliding_kernel" if args.fit == "Florinsky" and len(attrs) > 3
+                                    else "xbt::terrain_fused_kernel"),
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_pixel": bytes_per_px},
             "e2e": e2e, "cpu_baseline": cpu,
         }
