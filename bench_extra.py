@@ -181,16 +181,76 @@ def bench_nuthkaab(args) -> dict:
     }
 
 
+def bench_texture(args) -> dict:
+    """Texture shading: prepare -> rfft2 -> filter -> irfft2 -> finish on one GPU (the FFT is global:
+    replicas only, no row sharding)."""
+    import torch
+
+    from oracle import terrain_oracle as to
+    from xdem_b200 import _lib, freq
+
+    dev = torch.device("cuda", 0)
+    size = args.size
+    g = torch.Generator(device=dev).manual_seed(47)
+    z = torch.randn((size, size), generator=g, device=dev)
+    z = torch.cumsum(z, 0)
+    z = (1000.0 + 0.05 * torch.cumsum(z, 1)).float()
+    z[100:110, 200:230] = float("nan")
+    times = []
+    for rep in range(args.steps + 1):
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        out = freq.texture_shading_device(z, 0.8)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1) * 1e-3)
+        launches = _lib.launch_count() - l0
+        del out
+    dt = min(times[1:])
+    cs = min(args.cpu_size * 4, size)
+    zc = z[:cs, :cs].cpu().numpy()
+    to.texture_shading(zc[:256, :256], 0.8)
+    t0 = time.perf_counter()
+    to.texture_shading(zc, 0.8)
+    tcpu = time.perf_counter() - t0
+    peak = 6481.1
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    # algorithmic traffic of the five stages, float32: stats 4, pad 4+4, rfft2 >= 4+8*(1/2)*2.., counted as one read and
+    # one write of every array each stage touches: 4 + 8 + (4+4) + (4+4) + (4+4) + (8+4) = 48 B/px
+    algo = 48.0 * size * size
+    return {
+        "metric": "Mpixel/s texture shading (alpha 0.8)", "value": size * size / dt / 1e6, "unit": "Mpixel/s",
+        "n_gpus": 1, "steps": args.steps, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "replicas only",
+        "dtype": "f32 raster, complex64 spectrum, f64 filter", "data": "synthetic",
+        "config": {"workload": f"texture_shading {size}^2 float32 fractal DEM with a NaN hole, alpha 0.8 "
+                               f"({launches} library kernels of ours + 2 cuFFT transforms per step)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": algo / dt / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": algo / dt / 1e9 / peak,
+                     "note": "48 B/px = one read + one write per array per stage if each FFT were a single pass; cuFFT "
+                             "makes several passes over the 2-D data, so frac is a lower bound on its efficiency"},
+        "cpu_baseline": {"value": cs * cs / tcpu / 1e6, "unit": "Mpixel/s", "cores": 1, "kind": "port",
+                         "sample": f"{cs}^2 crop of the same DEM ({tcpu:.1f} s)",
+                         "what": "oracle/terrain_oracle.py:texture_shading (NumPy + scipy.fft restatement of "
+                                 "freq.py:62-148, pinned to reference fixtures)"},
+    }
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
-    ap.add_argument("workload", choices=["variogram", "nuthkaab"])
+    ap.add_argument("workload", choices=["variogram", "nuthkaab", "texture"])
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--cpu-n", type=int, default=40_000)
     ap.add_argument("--size", type=int, default=16384)
     ap.add_argument("--cpu-size", type=int, default=1024)
     args = ap.parse_args()
-    line = bench_variogram(args) if args.workload == "variogram" else bench_nuthkaab(args)
+    line = {"variogram": bench_variogram, "nuthkaab": bench_nuthkaab, "texture": bench_texture}[args.workload](args)
     if line:
         print(json.dumps(line), flush=True)
     import torch.distributed as dist

@@ -94,6 +94,28 @@ int xb_terrain_fused_host(const void* dem_host, int dtype, int64_t rows, int64_t
                           int64_t rows_per_block);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Texture shading (fractional Laplacian, Brown 2010) -- the device stages of `_texture_shading_fft`
+ * (xdem/terrain/freq.py:62-148; routed at terrain.py:641-643).  The two FFTs in between are plain library transforms
+ * issued by the caller (cuFFT through torch / CuPy; scipy.fft in the reference).
+ *   xb_texture_prepare  freq.py:84-112: stats_dev[0..2] = {sum, count} over non-NaN cells (np.nanmean) and the count of
+ *                       finite cells; padded[fft_rows x fft_cols] = symmetric pad of the DEM with non-finite cells
+ *                       replaced by that mean.  subtract_mean = 1 centres the raster on the mean first (same result for
+ *                       alpha > 0, whose filter zeroes the DC term; keeps float32 digits for the relief).  The caller
+ *                       checks stats[2] == 0 (all-NaN input -> all-NaN output).
+ *   xb_texture_filter   freq.py:114-137: in-place scale of the rfft2 half spectrum [fft_rows x (fft_cols/2+1)] complex
+ *                       by hypot(rfftfreq, fftfreq)^alpha evaluated in float64; DC term zeroed when alpha > 0.
+ *   xb_texture_finish   freq.py:142-146: crop the irfft2 result and restore NaN where the DEM was not finite.
+ * dtype 0 = float32 (complex64 spectrum), 1 = float64 (complex128).
+ */
+int xb_texture_prepare(const void* dem_dev, int dtype, int64_t rows, int64_t cols, int64_t ld, void* padded_dev,
+                       int64_t fft_rows, int64_t fft_cols, int64_t pad_rows, int64_t pad_cols, int subtract_mean,
+                       double* stats_dev, void* stream);
+int xb_texture_filter(void* spectrum_dev, int dtype, int64_t fft_rows, int64_t fft_cols, double alpha, void* stream);
+int xb_texture_finish(const void* padded_dev, int dtype, int64_t fft_rows, int64_t fft_cols, int64_t pad_rows,
+                      int64_t pad_cols, const void* dem_dev, int64_t rows, int64_t cols, int64_t ld, void* out_dev,
+                      int64_t out_ld, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Generic odd window (3..31) indexes and fractal roughness -- the reference's arbitrary `window_size`
  * (window.py:926-1002) and `fractal_roughness` (window.py:317-379, terrain.py:620-633).
  *  win_mask   bit 0 TPI, bit 1 TRI, bit 2 roughness, bit 4 fractal roughness (plane slots 0, 1, 2, 4 of a HOST array of

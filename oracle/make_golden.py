@@ -95,6 +95,28 @@ def main() -> None:
     nk_golden(ref)
 
 
+def texture_inputs() -> dict[str, np.ndarray]:
+    frac = synth.inject_nans(synth.fractal_dem((40, 52)), frac=0.004, hole=3)           # pads to 64 x 64
+    wide = synth.fractal_dem((30, 1100), seed=5)                                         # 1100 -> 1120 = 2^5 * 5 * 7
+    wide[3, 1000:1004] = np.nan
+    flat = np.full((17, 9), 123.5, dtype=np.float32)
+    allnan = np.full((6, 5), np.nan, dtype=np.float32)
+    return {"fractal": frac, "wide": wide, "fractal64": frac.astype(np.float64) + 0.123456789, "flat": flat,
+            "allnan": allnan}
+
+
+def texture_golden(ref) -> None:  # noqa
+    """Texture shading (freq.py:62-148) through the reference's public entry point, several exponents."""
+    gta = ref.terrain.get_terrain_attribute
+    store: dict[str, np.ndarray] = {}
+    for name, dem in texture_inputs().items():
+        store[f"in|{name}"] = dem
+        for alpha in (0.8, 1.5, 0.0, 2.0) if name in ("fractal", "fractal64") else (0.8,):
+            store[f"tex|{name}|{alpha}"] = gta(dem, "texture_shading", texture_alpha=alpha)
+    np.savez_compressed(os.path.join(OUT, "texture_reference.npz"), **store)
+    print(f"texture_reference.npz: {len(store)} arrays")
+
+
 def nk_golden(ref) -> None:  # noqa
     """Per-iteration outputs of the reference's own Nuth-Kaab code (affine.py:102-147, 477-609) on a synthetic pair."""
     import scipy.optimize
@@ -126,4 +148,11 @@ def nk_golden(ref) -> None:  # noqa
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+
+    if len(sys.argv) > 1 and sys.argv[1] == "texture":
+        warnings.filterwarnings("ignore")
+        texture_golden(load_reference())
+    else:
+        main()
+        texture_golden(load_reference())

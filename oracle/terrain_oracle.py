@@ -263,12 +263,64 @@ def _rugosity(z: np.ndarray, L: float, cd: np.dtype) -> np.ndarray:
     return area / (L * L)
 
 
+def next_fft_length(n: int) -> int:
+    """freq.py:33-59: power of two up to 1024, else the next integer whose only prime factors are 2, 3, 5, 7."""
+    if n <= 1:
+        return 1
+    if n <= 1024:
+        return int(2 ** np.ceil(np.log2(n)))
+    m = int(n)
+    while True:
+        r = m
+        for f in (2, 3, 5, 7):
+            while r % f == 0:
+                r //= f
+        if r == 1:
+            return m
+        m += 1
+
+
+def texture_shading(dem: np.ndarray, alpha: float | None = 0.8) -> np.ndarray:
+    """Restatement of ``_texture_shading_fft`` (freq.py:62-148): mean-fill of the non-finite cells (:84-94), symmetric
+    pad to the FFT size (:96-112), half-spectrum scaled by hypot(fx, fy)**alpha with the DC term set to 0 for alpha > 0
+    (:114-131), inverse transform, crop and NaN restore (:133-146).  scipy.fft keeps the input precision (float32
+    rasters are transformed in single precision, like the reference)."""
+    import scipy.fft as sfft
+
+    if alpha is None:
+        alpha = 0.8
+    if not 0 <= alpha <= 2:
+        raise ValueError(f"Alpha must be between 0 and 2, got {alpha}")
+    z = np.array(dem, copy=True)
+    ok = np.isfinite(z)
+    if not ok.any():
+        return np.full_like(z, np.nan)
+    if not ok.all():
+        z[~ok] = np.nanmean(dem)
+    n0, n1 = z.shape
+    m0, m1 = next_fft_length(n0), next_fft_length(n1)
+    b0, b1 = (m0 - n0) // 2, (m1 - n1) // 2
+    zp = np.pad(z, ((b0, m0 - n0 - b0), (b1, m1 - n1 - b1)), mode="symmetric")
+    mag = np.hypot(sfft.rfftfreq(m1)[None, :], sfft.fftfreq(m0)[:, None])
+    mag[0, 0] = 1.0
+    filt = mag ** alpha
+    if alpha > 0:
+        filt[0, 0] = 0.0
+    spec = sfft.rfft2(zp, s=(m0, m1))
+    spec *= filt
+    back = sfft.irfft2(spec, s=(m0, m1))
+    out = back[b0:b0 + n0, b1:b1 + n1].copy()
+    out[~ok] = np.nan
+    return out
+
+
 def get_terrain_attribute(dem: np.ndarray, attribute: list[str] | str, resolution: float = 1.0, degrees: bool = True,
                           hillshade_altitude: float = 45.0, hillshade_azimuth: float = 315.0,
                           hillshade_z_factor: float = 1.0, surface_fit: str = "Florinsky",
                           curv_method: str = "geometric", tri_method: str = "Riley", window_size: int = 3,
                           window_size_fractal: int = 13, out_dtype: np.dtype | None = None, coef_round: np.dtype | None = None,
-                          window_compute_dtype: np.dtype | None = None) -> list[np.ndarray] | np.ndarray:
+                          window_compute_dtype: np.dtype | None = None,
+                          texture_alpha: float = 0.8) -> list[np.ndarray] | np.ndarray:
     """Restatement of ``_get_terrain_attribute`` (terrain.py:528-666) for ndarray input: integer -> float32
     (:560-561), rad2deg in the array dtype (:586-591), hillshade clip (:594-596), request order (:651-658)."""
     single = isinstance(attribute, str)
@@ -299,5 +351,7 @@ def get_terrain_attribute(dem: np.ndarray, attribute: list[str] | str, resolutio
     if frac:
         res["fractal_roughness"] = windowed_indexes(dem, window_size_fractal, frac, resolution, tri_method, out_dtype,
                                                     window_compute_dtype)[0]
+    if "texture_shading" in attrs:
+        res["texture_shading"] = texture_shading(dem, texture_alpha).astype(out_dtype, copy=False)  # terrain.py:641-643
     out = [res[a] for a in attrs]
     return out[0] if single else out

@@ -79,8 +79,6 @@ def test_out_of_scope_attributes_fail_loudly() -> None:
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         with pytest.raises(NotImplementedError):
-            t.texture_shading(dem)
-        with pytest.raises(NotImplementedError):
             t.roughness(dem, window_size=33)
         with pytest.raises(NotImplementedError):
             t.roughness(dem, window_size=4)

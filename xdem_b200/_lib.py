@@ -76,6 +76,14 @@ def lib() -> ctypes.CDLL:
                                   c_void_p]
     L.xb_nk_next_keys.restype = c_int
     L.xb_nk_next_keys.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]
+    L.xb_texture_prepare.restype = c_int
+    L.xb_texture_prepare.argtypes = [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64,
+                                     c_int64, c_int, c_void_p, c_void_p]
+    L.xb_texture_filter.restype = c_int
+    L.xb_texture_filter.argtypes = [c_void_p, c_int, c_int64, c_int64, c_double, c_void_p]
+    L.xb_texture_finish.restype = c_int
+    L.xb_texture_finish.argtypes = [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64,
+                                    c_int64, c_void_p, c_int64, c_void_p]
     _lib = L
     return L
 
@@ -98,6 +106,7 @@ def launch_count() -> int:
 EXPORTED = ["xb_last_error", "xb_version", "xb_launch_count", "xb_terrain_fused", "xb_terrain_fused_host",
             "xb_variogram_group_size", "xb_variogram_chunk", "xb_variogram_pairs", "xb_variogram_median_pass", "xb_variogram_maxd2", "xb_nk_aux",
             "xb_nk_dh", "xb_nk_hist", "xb_nk_next", "xb_nk_make_keys", "xb_nk_hist_keys", "xb_nk_next_keys",
-            "xb_windowed_generic", "xb_set_option", "xb_shift_resample"]
+            "xb_windowed_generic", "xb_set_option", "xb_shift_resample", "xb_texture_prepare", "xb_texture_filter",
+            "xb_texture_finish"]
 
 __all__ = ["lib", "check", "launch_count", "set_option", "XdemB200Error", "LIB_PATH", "EXPORTED"]

@@ -189,11 +189,6 @@ def _get_terrain_attribute(
     win = list(dict.fromkeys(a for a in attribute if a in list_requiring_windowed_index))
     frac = [a for a in attribute if a in list_requiring_windowed_fractal_index]
     other = [a for a in attribute if a in list_requiring_frequency_domain]
-    if other:
-        raise NotImplementedError(
-            f"{other} is not on the B200 hot path (SURVEY.md section 8f rank 4: global FFT); use the reference CPU "
-            "implementation for it."
-        )
     for ws in ([window_size] if win else []) + ([window_size_fractal] if frac else []):
         if ws < 3 or ws > 31 or ws % 2 == 0:
             raise NotImplementedError(f"the B200 engine supports odd window sizes between 3 and 31 (got {ws})")
@@ -203,7 +198,7 @@ def _get_terrain_attribute(
     fused_win = [a for a in win if (window_size in (3, 5) and not (a == "rugosity" and window_size != 3))]
     rug_separate = "rugosity" in win and "rugosity" not in fused_win
     generic_win = [a for a in win if a not in fused_win and a != "rugosity"]
-    needs_device = bool(generic_win or frac or rug_separate)
+    needs_device = bool(generic_win or frac or rug_separate or other)
 
     is_raster = _arrays.is_raster_like(dem)
     kwargs = dict(surface_fit=surface_fit, curv_method=curv_method, tri_method=tri_method, degrees=degrees,
@@ -226,6 +221,11 @@ def _get_terrain_attribute(
             planes.update({a: out[i] for i, a in enumerate(generic_win)})
         if frac:
             planes["fractal_roughness"] = _engine.windowed_generic(t, window_size_fractal, ["fractal_roughness"])[0]
+        if other:
+            # terrain.py:641-643: global frequency-domain attribute (cuFFT + the xb_texture_* kernels)
+            from xdem_b200 import freq
+
+            planes["texture_shading"] = freq.texture_shading_device(t, texture_alpha)
         kind = "torch" if on_device else "numpy"
         outs = [_arrays.from_device(planes[a], kind, out_dtype) for a in attribute]
         if as_tensor and not on_device:
@@ -376,7 +376,7 @@ def fractal_roughness(dem: Any, window_size_fractal: int = 13, mp_config: Any = 
 
 
 def texture_shading(dem: Any, alpha: float = 0.8, mp_config: Any = None) -> Any:
-    """terrain.py:1783-1838 -- out of scope (global FFT): raises NotImplementedError."""
+    """terrain.py:1783-1838: texture shaded relief (fractional Laplacian, exponent `alpha` in [0, 2])."""
     return get_terrain_attribute(dem=dem, attribute="texture_shading", texture_alpha=alpha, mp_config=mp_config)
 
 
