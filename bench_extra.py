@@ -241,16 +241,70 @@ def bench_texture(args) -> dict:
     }
 
 
+def bench_binning(args) -> dict:
+    """nd_binning core: count + exact median + NMAD of a dh-like raster in 100 bins of one terrain
+    variable (TerrainBias' default binning, biascorr.py:467-473) -- bin numbers + 2 x 4 radix-select passes."""
+    import torch
+
+    from oracle import binning_oracle as bo
+    from xdem_b200 import _lib, binning as xb
+
+    dev = torch.device("cuda", 0)
+    n = args.size * args.size
+    g = torch.Generator(device=dev).manual_seed(48)
+    var = torch.randn(n, generator=g, device=dev) * 1.5
+    vals = 0.3 * var + torch.randn(n, generator=g, device=dev) * 0.5
+    edges = xb.bin_edges(float(var.min()), float(var.max()), 100, np.float32)
+    times = []
+    for rep in range(args.steps + 1):
+        l0 = _lib.launch_count()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st = xb.binned_robust_stats(vals, [var], [edges], want_nmad=True)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+        launches = _lib.launch_count() - l0
+    dt = min(times[1:])
+    assert int(st["count"].sum()) == n
+    m = min(n, args.cpu_size * args.cpu_size * 4)
+    vc, xc = vals[:m].cpu().numpy(), var[:m].cpu().numpy()
+    t0 = time.perf_counter()
+    bo.nd_binning(vc, [xc], [100])
+    tcpu = time.perf_counter() - t0
+    peak = 6481.1
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    algo = (8 + 6) * n + 2 * 4 * 6.0 * n  # keys pass (8 B read, 6 B written) + 8 select passes over 6-byte pairs
+    return {
+        "metric": "Msamples/s binned count + median + NMAD (100 bins, 1 variable)", "value": n / dt / 1e6,
+        "unit": "Msample/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "replicas only", "dtype": "f32 values, u32 keys, u16 bin numbers, exact selects", "data": "synthetic",
+        "config": {"workload": f"{n} samples ({args.size}^2 raster), 100 linspace bins, statistics count / nanmedian / "
+                               f"nmad ({launches} kernel launches, 10 host round trips for the radix digits)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": algo / dt / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": algo / dt / 1e9 / peak,
+                     "note": "14 B/sample for the key pass + 8 radix passes x 6 B/sample (+ absdev re-key 10 B)"},
+        "cpu_baseline": {"value": m / tcpu / 1e6, "unit": "Msample/s", "cores": 1, "kind": "port",
+                         "sample": f"first {m} samples ({tcpu:.1f} s)",
+                         "what": "oracle/binning_oracle.py (scipy.stats.binned_statistic_dd with np.nanmedian and nmad, the "
+                                 "calls the reference makes)"},
+    }
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
-    ap.add_argument("workload", choices=["variogram", "nuthkaab", "texture"])
+    ap.add_argument("workload", choices=["variogram", "nuthkaab", "texture", "binning"])
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--cpu-n", type=int, default=40_000)
     ap.add_argument("--size", type=int, default=16384)
     ap.add_argument("--cpu-size", type=int, default=1024)
     args = ap.parse_args()
-    line = {"variogram": bench_variogram, "nuthkaab": bench_nuthkaab, "texture": bench_texture}[args.workload](args)
+    line = {"variogram": bench_variogram, "nuthkaab": bench_nuthkaab, "texture": bench_texture,
+            "binning": bench_binning}[args.workload](args)
     if line:
         print(json.dumps(line), flush=True)
     import torch.distributed as dist

@@ -94,6 +94,29 @@ int xb_terrain_fused_host(const void* dem_host, int dtype, int64_t rows, int64_t
                           int64_t rows_per_block);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * N-D binned robust statistics -- the device side of `nd_binning` (xdem/spatialstats.py:91-216), i.e. of the
+ * `scipy.stats.binned_statistic[_2d|_dd]` calls it makes with `statistic = "count" / np.nanmedian / nmad`.
+ *   xb_bin_keys         bin number (np.digitize per variable against its edges, last edge closed with SciPy's rounding
+ *                       rule p10 = 10^decimal, out-of-range or non-finite samples -> 0xFFFF; C-order flattening) and the
+ *                       order-preserving 32-bit key of every value.  1..3 variables; vars_dev_host / n_edges_host /
+ *                       p10_host are HOST arrays of n_dims entries; edges_dev = the edge arrays concatenated (float64
+ *                       copies of the sample-dtype edges SciPy would build).
+ *   xb_bin_hist         histogram (n_bins x 256 u64) of one 8-bit digit of the keys whose masked bits equal their bin's
+ *                       prefix: one pass of the MSD radix select that finds every bin's exact median.
+ *   xb_bin_next         per bin the smallest key > sel[bin] (next_key_dev pre-set to 0xFFFFFFFF): upper middle value.
+ *   xb_bin_absdev_keys  keys of |value - center[bin]| in float32 arithmetic: the NMAD's second select.
+ */
+int xb_bin_keys(const float* values_dev, const float* const* vars_dev_host, int n_dims, int64_t n,
+                const double* edges_dev, const int32_t* n_edges_host, const double* p10_host, uint32_t* key_dev,
+                uint16_t* bin_dev, void* stream);
+int xb_bin_hist(const uint32_t* key_dev, const uint16_t* bin_dev, int64_t n, int n_bins, const uint32_t* prefix_dev,
+                uint32_t prefix_mask, int shift, unsigned long long* hist_dev, void* stream);
+int xb_bin_next(const uint32_t* key_dev, const uint16_t* bin_dev, int64_t n, int n_bins, const uint32_t* sel_dev,
+                uint32_t* next_key_dev, void* stream);
+int xb_bin_absdev_keys(const float* values_dev, const uint16_t* bin_dev, int64_t n, int n_bins,
+                       const float* center_dev, uint32_t* key_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Texture shading (fractional Laplacian, Brown 2010) -- the device stages of `_texture_shading_fft`
  * (xdem/terrain/freq.py:62-148; routed at terrain.py:641-643).  The two FFTs in between are plain library transforms
  * issued by the caller (cuFFT through torch / CuPy; scipy.fft in the reference).

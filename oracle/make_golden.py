@@ -117,6 +117,49 @@ def texture_golden(ref) -> None:  # noqa
     print(f"texture_reference.npz: {len(store)} arrays")
 
 
+def binning_inputs() -> dict[str, np.ndarray]:
+    """dh-like values with three explanatory variables (slope-, curvature-, elevation-like), NaNs in each."""
+    rng = np.random.default_rng(77)
+    n = 20000
+    slope = rng.gamma(2.0, 8.0, n).astype(np.float32)
+    curv = rng.normal(0, 1.5, n).astype(np.float32)
+    elev = rng.uniform(900, 2600, n).astype(np.float32)
+    vals = (0.02 * slope * rng.normal(size=n) + 0.3 * curv + rng.normal(0, 0.5, n)).astype(np.float32)
+    vals[rng.choice(n, 150, replace=False)] = np.nan
+    slope[rng.choice(n, 90, replace=False)] = np.nan
+    curv[rng.choice(n, 60, replace=False)] = np.nan
+    vals[:40] = np.round(vals[:40])  # ties
+    return {"values": vals, "slope": slope, "curv": curv, "elev": elev}
+
+
+def binning_golden(ref) -> None:  # noqa
+    """`nd_binning` of the unmodified reference (spatialstats.py:91-216): default statistics (count, nanmedian, nmad),
+    integer bin counts and explicit edges, 1, 2 and 3 variables.  DataFrame columns are stored as arrays."""
+    nd = ref.spatialstats.nd_binning
+    I = binning_inputs()
+    store: dict[str, np.ndarray] = {f"in|{k}": v for k, v in I.items()}
+
+    def put(tag: str, df) -> None:  # noqa
+        store[f"{tag}|nd"] = df["nd"].to_numpy().astype(np.int64)
+        for col in ("count", "nanmedian", "nmad"):
+            store[f"{tag}|{col}"] = df[col].to_numpy().astype(np.float64)
+        for name in ("slope", "curv", "elev"):
+            if name in df.columns:
+                left = np.array([iv.left if hasattr(iv, "left") else np.nan for iv in df[name]], dtype=np.float64)
+                right = np.array([iv.right if hasattr(iv, "right") else np.nan for iv in df[name]], dtype=np.float64)
+                store[f"{tag}|{name}|left"], store[f"{tag}|{name}|right"] = left, right
+
+    put("one10", nd(I["values"], [I["slope"]], ["slope"], list_var_bins=10))
+    put("two", nd(I["values"], [I["slope"], I["curv"]], ["slope", "curv"], list_var_bins=(8, 5)))
+    edges = (np.array([0, 5, 10, 20, 40, 90], dtype=np.float32), np.array([-5, -1, 0, 1, 5], dtype=np.float32),
+             np.array([800, 1500, 2000, 2700], dtype=np.float32))
+    put("three_edges", nd(I["values"], [I["slope"], I["curv"], I["elev"]], ["slope", "curv", "elev"],
+                          list_var_bins=edges))
+    put("three_int", nd(I["values"], [I["slope"], I["curv"], I["elev"]], ["slope", "curv", "elev"], list_var_bins=4))
+    np.savez_compressed(os.path.join(OUT, "binning_reference.npz"), **store)
+    print(f"binning_reference.npz: {len(store)} arrays")
+
+
 def nk_golden(ref) -> None:  # noqa
     """Per-iteration outputs of the reference's own Nuth-Kaab code (affine.py:102-147, 477-609) on a synthetic pair."""
     import scipy.optimize
@@ -150,9 +193,12 @@ def nk_golden(ref) -> None:  # noqa
 if __name__ == "__main__":
     import sys
 
+    warnings.filterwarnings("ignore")
     if len(sys.argv) > 1 and sys.argv[1] == "texture":
-        warnings.filterwarnings("ignore")
         texture_golden(load_reference())
+    elif len(sys.argv) > 1 and sys.argv[1] == "binning":
+        binning_golden(load_reference())
     else:
         main()
         texture_golden(load_reference())
+        binning_golden(load_reference())

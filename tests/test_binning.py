@@ -1,0 +1,162 @@
+"""`nd_binning`: SciPy-based oracle vs fixtures of the unmodified reference (CPU), the CUDA
+path vs both (GPU).  Counts are integers (exact); medians / NMADs are order statistics of float32 data (exact selects),
+compared at 1e-6 relative to absorb the float32-vs-float64 mean of two middle values."""
+
+from __future__ import annotations
+
+import itertools
+
+import numpy as np
+import pytest
+
+from tests import parity
+
+NAMES = ["slope", "curv", "elev"]
+CASES = {
+    "one10": (["slope"], 10),
+    "two": (["slope", "curv"], (8, 5)),
+    "three_edges": (NAMES, (np.array([0, 5, 10, 20, 40, 90], dtype=np.float32),
+                            np.array([-5, -1, 0, 1, 5], dtype=np.float32),
+                            np.array([800, 1500, 2000, 2700], dtype=np.float32))),
+    "three_int": (NAMES, 4),
+}
+
+
+@pytest.fixture(scope="module")
+def B() -> dict[str, np.ndarray]:
+    return parity.load_golden("binning_reference.npz")
+
+
+def _combos(n: int) -> list[tuple[int, ...]]:
+    c: list[tuple[int, ...]] = [(i,) for i in range(n)]
+    if n > 1:
+        c += list(itertools.combinations(range(n), 2))
+    if n > 2:
+        c.append(tuple(range(n)))
+    return c
+
+
+def _close(a: np.ndarray, b: np.ndarray, msg: str) -> None:
+    assert a.shape == b.shape, msg
+    assert np.array_equal(np.isnan(a), np.isnan(b)), f"{msg}: NaN pattern"
+    m = np.isfinite(b)
+    assert np.allclose(a[m], b[m], rtol=1e-6, atol=1e-7), f"{msg}: max diff {np.max(np.abs(a[m] - b[m]))}"
+
+
+def test_oracle_matches_reference_fixtures(B) -> None:
+    from oracle import binning_oracle as bo
+
+    for tag, (names, bins) in CASES.items():
+        lv = [B[f"in|{n}"] for n in names]
+        lb = list(bins) if isinstance(bins, tuple) else [bins] * len(names)
+        res = bo.nd_binning(B["in|values"], lv, lb)
+        cnt = np.concatenate([res[c]["count"] for c in _combos(len(names))])
+        med = np.concatenate([res[c]["median"] for c in _combos(len(names))])
+        nm = np.concatenate([res[c]["nmad"] for c in _combos(len(names))])
+        assert np.array_equal(cnt, B[f"{tag}|count"]), tag
+        _close(med, B[f"{tag}|nanmedian"], f"{tag} median")
+        _close(nm, B[f"{tag}|nmad"], f"{tag} nmad")
+
+
+def test_host_helpers() -> None:
+    from xdem_b200 import binning as xb
+
+    e = xb.bin_edges(1.0, 3.0, 4, np.float32)
+    assert e.dtype == np.float32 and np.array_equal(e, np.linspace(1, 3, 5, dtype=np.float32))
+    assert np.array_equal(xb.bin_edges(2.0, 2.0, 2, np.float32), np.array([1.5, 2.0, 2.5], dtype=np.float32))
+    assert np.array_equal(xb.bin_edges(0, 0, [0, 1, 5], np.float32), np.array([0, 1, 5], dtype=np.float32))
+    hist = np.array([[0, 3, 0, 2], [1, 1, 1, 1], [0, 0, 0, 0]])
+    counts = hist.sum(axis=1)
+    digit, below = xb._pick_digit(hist, np.array([3, 1, 0]), counts)
+    assert digit.tolist() == [3, 1, 0] and below.tolist() == [3, 1, 0]
+    assert np.array_equal(xb._key_to_float(np.array([0x80000000 | np.float32(1.5).view(np.uint32)], dtype=np.uint32)),
+                          np.array([1.5], dtype=np.float32))
+    with pytest.raises(NotImplementedError, match="arbitrary Python callable"):
+        xb._stat_kind(np.nanstd)
+    assert xb._stat_kind(np.nanmedian) == ("nanmedian", "median")
+    assert xb._stat_kind(xb.nmad) == ("nmad", "nmad")
+
+
+# ---------------------------------------------------------------------------------------------------------- GPU
+
+
+@pytest.mark.gpu
+def test_gpu_nd_binning_vs_reference_fixtures(B) -> None:
+    from xdem_b200 import spatialstats as xs
+
+    for tag, (names, bins) in CASES.items():
+        lv = [B[f"in|{n}"] for n in names]
+        df = xs.nd_binning(B["in|values"], lv, list(names), list_var_bins=bins)
+        assert np.array_equal(df["nd"].to_numpy(), B[f"{tag}|nd"]), tag
+        assert np.array_equal(df["count"].to_numpy(), B[f"{tag}|count"]), tag
+        _close(df["nanmedian"].to_numpy(), B[f"{tag}|nanmedian"], f"{tag} median")
+        _close(df["nmad"].to_numpy(), B[f"{tag}|nmad"], f"{tag} nmad")
+        for n in names:
+            left = np.array([iv.left if hasattr(iv, "left") else np.nan for iv in df[n]], dtype=np.float64)
+            right = np.array([iv.right if hasattr(iv, "right") else np.nan for iv in df[n]], dtype=np.float64)
+            assert np.array_equal(left, B[f"{tag}|{n}|left"], equal_nan=True), (tag, n)
+            assert np.array_equal(right, B[f"{tag}|{n}|right"], equal_nan=True), (tag, n)
+
+
+@pytest.mark.gpu
+def test_gpu_statistics_selection_and_edges() -> None:
+    import torch
+
+    from oracle import binning_oracle as bo
+    from xdem_b200 import spatialstats as xs
+
+    rng = np.random.default_rng(3)
+    v = rng.normal(size=5000).astype(np.float32)
+    x = rng.uniform(0, 1, 5000).astype(np.float32)
+    x[:3] = [0.0, 1.0, 1.0]  # samples on the first and on the (closed) last edge
+    df = xs.nd_binning(torch.from_numpy(v).cuda(), [torch.from_numpy(x).cuda()], ["x"], list_var_bins=[[0, 0.25, 0.5, 1.0]],
+                       statistics=["count", "median"])
+    assert list(df.columns) == ["nd", "count", "median", "x"]
+    ref = bo.nd_binning(v, [x], [np.array([0, 0.25, 0.5, 1.0], dtype=np.float32)], with_nmad=False)[(0,)]
+    assert np.array_equal(df["count"].to_numpy(), ref["count"]) and int(df["count"].sum()) == 5000
+    _close(df["median"].to_numpy(), ref["median"], "median")
+    # count is always added; even bins with an even number of samples and heavy ties
+    v2 = np.repeat(np.array([1.0, 2.0, 2.0, 7.0], dtype=np.float32), 50)
+    x2 = np.tile(np.array([0.1, 0.6], dtype=np.float32), 100)
+    df2 = xs.nd_binning(v2, [x2], ["x"], list_var_bins=2, statistics=[np.nanmedian, xs.nmad])
+    ref2 = bo.nd_binning(v2, [x2], [2])[(0,)]
+    assert list(df2.columns) == ["nd", "count", "nanmedian", "nmad", "x"]
+    _close(df2["nanmedian"].to_numpy(), ref2["median"], "ties median")
+    _close(df2["nmad"].to_numpy(), ref2["nmad"], "ties nmad")
+    assert xs.nmad(v) == pytest.approx(float(bo.nmad(v)), rel=1e-6)
+    with pytest.raises(NotImplementedError):
+        xs.nd_binning(v, [x], ["x"], statistics=[np.nanstd])
+
+
+@pytest.mark.gpu
+def test_gpu_binning_large_properties() -> None:
+    """5e7 samples, 20 x 20 bins (global-memory histograms: 400 bins exceed the shared-memory variant): every sample is
+    counted once in each binning; medians of a value that only depends on the bin are that value; shuffling the samples
+    changes nothing."""
+    import torch
+
+    from xdem_b200 import binning as xb
+
+    g = torch.Generator(device="cuda").manual_seed(8)
+    n = 50_000_000
+    x = torch.rand(n, generator=g, device="cuda")
+    y = torch.rand(n, generator=g, device="cuda")
+    ex = np.linspace(0, 1, 21, dtype=np.float32)
+    ix = torch.clamp((x * 20).floor(), max=19)
+    iy = torch.clamp((y * 20).floor(), max=19)
+    # recompute the bin from the float32 edges actually used (x*20 can differ from the edge compare by an ulp)
+    ext = torch.from_numpy(ex).cuda()
+    ix = torch.clamp(torch.bucketize(x, ext, right=True) - 1, 0, 19).float()
+    iy = torch.clamp(torch.bucketize(y, ext, right=True) - 1, 0, 19).float()
+    v = ix * 100 + iy + 0.25
+    st = xb.binned_robust_stats(v, [x, y], [ex, ex], want_nmad=True)
+    assert int(st["count"].sum()) == n
+    want = (np.arange(20)[:, None] * 100 + np.arange(20)[None, :] + 0.25).ravel().astype(np.float32)
+    assert np.array_equal(st["median"], want) and np.all(st["nmad"] == 0)
+    perm = torch.randperm(n, generator=g, device="cuda")
+    noise = torch.randn(n, generator=g, device="cuda")
+    a = xb.binned_robust_stats(noise, [x, y], [ex, ex], want_nmad=True)
+    b = xb.binned_robust_stats(noise[perm], [x[perm], y[perm]], [ex, ex], want_nmad=True)
+    for k in ("count", "median", "nmad"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.allclose(a["median"], 0.0, atol=0.02) and np.allclose(a["nmad"], 1.0, atol=0.02)  # N(0,1): nmad ~ sigma

@@ -3,7 +3,8 @@
 * ``xdem_b200.terrain``      -- drop-in for ``xdem.terrain`` (get_terrain_attribute + wrappers), one fused CUDA pass
 * ``xdem_b200.surfit/window``-- the reference's engine seam functions (``_get_surface_attributes`` /
                                 ``_get_windowed_indexes``)
-* ``xdem_b200.spatialstats`` -- ``sample_empirical_variogram`` (all-pairs lag binning on the GPU)
+* ``xdem_b200.spatialstats`` -- ``sample_empirical_variogram`` (all-pairs lag binning on the GPU), ``nd_binning``
+* ``xdem_b200.freq``         -- texture shading (our kernels around two cuFFT transforms)
 * ``xdem_b200.coreg``        -- ``NuthKaab`` / ``nuth_kaab`` (slope/aspect + aspect-binned medians on the GPU)
 * ``xdem_b200.distributed``  -- row-sharded multi-GPU drivers (NCCL halo exchange / histogram all-reduce)
 * ``xdem_b200.install()``    -- rebinds the seam inside an importable ``xdem`` so DEM.slope() etc. run on the GPU

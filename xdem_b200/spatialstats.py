@@ -19,6 +19,7 @@ import pandas as pd
 import torch
 
 from . import _arrays, _lib
+from .binning import nd_binning, nmad  # noqa: F401  (spatialstats.py:76-216 of the reference)
 
 _METHODS = ["cdist_equidistant", "cdist_point", "pdist_point", "pdist_disk", "pdist_ring"]
 
