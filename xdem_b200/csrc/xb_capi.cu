@@ -23,6 +23,8 @@ void xb_count_launch(int n) { g_launches.fetch_add((unsigned long long)n); }
 
 static std::atomic<int> g_opt_fl_generic{0};
 bool xb_option_florinsky_generic() { return g_opt_fl_generic.load() != 0; }
+static std::atomic<int> g_opt_fl_packed{1};
+bool xb_option_florinsky_packed() { return g_opt_fl_packed.load() != 0; }
 static std::atomic<int> g_opt_vg_full{7};
 int xb_option_variogram_full_tiles() { return g_opt_vg_full.load(); }
 
@@ -155,6 +157,10 @@ uint64_t xb_launch_count(void) { return g_launches.load(); }
 int xb_set_option(const char* name, int value) {
     if (name && strcmp(name, "florinsky_generic") == 0) {
         g_opt_fl_generic.store(value);
+        return XB_OK;
+    }
+    if (name && strcmp(name, "florinsky_packed") == 0) {
+        g_opt_fl_packed.store(value);
         return XB_OK;
     }
     if (name && strcmp(name, "variogram_full_tiles") == 0) {

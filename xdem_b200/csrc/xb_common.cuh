@@ -87,4 +87,5 @@ typedef CUresult (*xb_cuTensorMapEncodeTiled_t)(CUtensorMap*, CUtensorMapDataTyp
 xb_cuTensorMapEncodeTiled_t xb_get_tensormap_encoder();
 int xb_num_sms(int* out);
 bool xb_option_florinsky_generic();
+bool xb_option_florinsky_packed();   // f32x2 (FFMA2) arithmetic in the sliding Florinsky kernel
 int xb_option_variogram_full_tiles();  // bit k-1: interior tiles spanning k lag classes take the threshold-light sweep

@@ -19,6 +19,8 @@
 // <= 1e-6 relative against the generic kernel / reference fixtures).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "xb_terrain_dev.cuh"
 
 namespace xbt {
@@ -147,7 +149,136 @@ __device__ __forceinline__ void emit_row(const RowFeat& r0, const RowFeat& r1, c
     }
 }
 
-template <bool ALG, unsigned CMASK>
+// ---------------------------------------------------------------------------------------------------------------
+// Packed variant: the two pixels of a lane ride in one f32x2 register pair and the arithmetic uses sm_100's packed
+// FADD2 / FMUL2 / FFMA2 (crt/sm_100_rt.h).  A packed op occupies the FMA pipe for two cycles (micro-benchmark
+// scripts/micro/ffma2_bench.cu: 106 vs 120 scalar-FMA lanes/clk/SM) but takes ONE issue slot -- and this kernel is
+// issue-bound (ncu r01c: 85 % issue-active, FMA pipe 67 %).  Same formulas as emit_row; second derivatives are carried
+// negated (nsxx = -z_xx sums, nsyy) so that every subtraction is a single FFMA2 with a -1 / -2 constant (packed ops have
+// no operand-negate modifier).  MUFU seeds, min/max and the quadrant selects stay scalar.
+// ---------------------------------------------------------------------------------------------------------------
+using f2 = float2;
+__device__ __forceinline__ f2 S2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return __ffma2_rn(b, S2(-1.0f), a); }  // a - b, one rounding
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+
+struct RowFeat2 {
+    f2 p, q, D, E, c;
+};
+
+__device__ __forceinline__ void make_features(const float* row, RowFeat2& f) {
+    const f2 a = *reinterpret_cast<const f2*>(row);      // w[0], w[1]
+    const f2 b = *reinterpret_cast<const f2*>(row + 2);  // w[2], w[3]  = the two centres
+    const f2 d = *reinterpret_cast<const f2*>(row + 4);  // w[4], w[5]
+    const f2 m1 = make_float2(a.y, b.x);                  // w[k+1]
+    const f2 m3 = make_float2(b.y, d.x);                  // w[k+3]
+    f.c = b;
+    f.p = add2(sub2(a, b), sub2(d, b));
+    f.q = add2(sub2(m1, b), sub2(m3, b));
+    f.D = sub2(d, a);
+    f.E = sub2(m1, m3);
+}
+
+// atan(t), t in [0,1], both components (same polynomial as xbm::atan_unit)
+__device__ __forceinline__ f2 atan_unit2(f2 t) {
+    const f2 z = mul2(t, t);
+    f2 q = S2(2.8423242409e-03f);
+    q = fma2(q, z, S2(-1.6053270867e-02f));
+    q = fma2(q, z, S2(4.2698739575e-02f));
+    q = fma2(q, z, S2(-7.5086833966e-02f));
+    q = fma2(q, z, S2(1.0645598343e-01f));
+    q = fma2(q, z, S2(-1.4205896306e-01f));
+    q = fma2(q, z, S2(1.9993145739e-01f));
+    q = fma2(q, z, S2(-3.3333126241e-01f));
+    return fma2(mul2(t, z), q, t);
+}
+
+template <unsigned CMASK, bool FAST>
+__device__ __forceinline__ void emit_row(const RowFeat2& r0, const RowFeat2& r1, const RowFeat2& r2, const RowFeat2& r3,
+                                         const RowFeat2& r4, const TerrainParams& p, long long off, bool full,
+                                         int nvalid) {
+    static_assert(CMASK != 0 && (CMASK & ~15u) == 0, "packed path: compile-time mask without the curvature algebra");
+    // z_x (fl_p, divider 420 res)
+    f2 sx = mul2(S2(31.0f), add2(r0.D, r4.D));
+    sx = fma2(S2(-5.0f), add2(r1.D, r3.D), sx);
+    sx = fma2(S2(-17.0f), r2.D, sx);
+    sx = fma2(S2(44.0f), add2(r0.E, r4.E), sx);
+    sx = fma2(S2(62.0f), add2(r1.E, r3.E), sx);
+    sx = fma2(S2(68.0f), r2.E, sx);
+    // z_y (fl_q)
+    const f2 t1 = fma2(S2(-5.0f), sub2(r0.q, r4.q), mul2(S2(31.0f), sub2(r0.p, r4.p)));
+    const f2 t2 = fma2(S2(62.0f), sub2(r3.q, r1.q), mul2(S2(44.0f), sub2(r3.p, r1.p)));
+    const f2 t3 = fma2(S2(280.0f), sub2(r3.c, r1.c), mul2(S2(35.0f), sub2(r0.c, r4.c)));
+    const f2 sy = add2(add2(t1, t2), t3);
+    const f2 pp2 = add2(r0.p, r4.p), pp1 = add2(r1.p, r3.p);
+    const f2 qq2 = add2(r0.q, r4.q), qq1 = add2(r1.q, r3.q);
+    const f2 sp = add2(add2(pp2, pp1), r2.p), sq = add2(add2(qq2, qq1), r2.q);
+    const f2 nsxx = fma2(S2(-2.0f), sp, sq);  // -(2 sp - sq): touches every cell of the window
+    const f2 car = mul2(nsxx, S2(0.0f));
+    if (CMASK & 7u) {
+        const float inv1 = (float)p.inv_d1;
+        const f2 zx = mul2(sx, S2(inv1)), zy = mul2(sy, S2(inv1));
+        const f2 g2 = fma2(zx, zx, mul2(zy, zy));
+        const float ang = p.degrees ? (float)p.rad2deg : 1.0f;
+        if (CMASK & 1u) {
+            // sqrt_fast on both components: r = rsqrt(max(x, tiny)); g = x r; g += (0.5 r)(x - g g)
+            const f2 r = make_float2(xbm::rsqrt_approx(fmaxf(g2.x, 1.17549435e-38f)),
+                                     xbm::rsqrt_approx(fmaxf(g2.y, 1.17549435e-38f)));
+            f2 g = mul2(g2, r);
+            const f2 e = fma2(mul2(g, S2(-1.0f)), g, g2);
+            g = fma2(mul2(r, S2(0.5f)), e, g);
+            // atan_pos
+            const bool b0 = g.x > 1.0f, b1 = g.y > 1.0f;
+            const f2 t = make_float2(b0 ? xbm::rcp_approx(g.x) : g.x, b1 ? xbm::rcp_approx(g.y) : g.y);
+            const f2 a = atan_unit2(t);
+            const f2 v = make_float2(b0 ? xbm::HALF_PI_F - a.x : a.x, b1 ? xbm::HALF_PI_F - a.y : a.y);
+            const f2 o = fma2(v, S2(ang), car);
+            store2<FAST>(p.out[0], off, full, nvalid, o.x, o.y);
+        }
+        if (CMASK & 2u) {
+            const float ax0 = fabsf(zx.x), ay0 = fabsf(zy.x), ax1 = fabsf(zx.y), ay1 = fabsf(zy.y);
+            const f2 mn = make_float2(fminf(ax0, ay0), fminf(ax1, ay1));
+            const f2 rc = make_float2(xbm::rcp_approx(fmaxf(fmaxf(ax0, ay0), 1.17549435e-38f)),
+                                      xbm::rcp_approx(fmaxf(fmaxf(ax1, ay1), 1.17549435e-38f)));
+            const f2 a = atan_unit2(mul2(mn, rc));
+            float v0 = a.x, v1 = a.y;
+            v0 = ax0 > ay0 ? xbm::HALF_PI_F - v0 : v0;
+            v1 = ax1 > ay1 ? xbm::HALF_PI_F - v1 : v1;
+            v0 = zy.x < 0.0f ? xbm::PI_F - v0 : v0;
+            v1 = zy.y < 0.0f ? xbm::PI_F - v1 : v1;
+            v0 = zx.x < 0.0f ? xbm::TWO_PI_F - v0 : v0;
+            v1 = zx.y < 0.0f ? xbm::TWO_PI_F - v1 : v1;
+            const f2 o = fma2(make_float2(v0, v1), S2(ang), car);
+            store2<FAST>(p.out[1], off, full, nvalid, o.x, o.y);
+        }
+        if (CMASK & 4u) {
+            const float ky = (float)p.hs_ky, kx = -(float)p.hs_kx, sa = (float)p.hs_sin_alt, zf2 = (float)p.zf2;
+            const float lo = p.clip_hs ? 0.0f : -CUDART_INF_F, hi = p.clip_hs ? 255.0f : CUDART_INF_F;
+            const f2 den = fma2(S2(zf2), g2, S2(1.0f));
+            const f2 r = make_float2(xb_rsqrt(den.x), xb_rsqrt(den.y));
+            const f2 inner = fma2(S2(ky), zy, fma2(S2(kx), zx, S2(sa)));
+            const f2 h = fma2(mul2(S2(254.0f), r), inner, S2(1.5f));
+            const f2 hc = make_float2(fminf(fmaxf(h.x, lo), hi), fminf(fmaxf(h.y, lo), hi));
+            const f2 o = add2(hc, car);
+            store2<FAST>(p.out[2], off, full, nvalid, o.x, o.y);
+        }
+    }
+    if (CMASK & 8u) {
+        // -z_yy sums: (pp1 - 2 (pp2 - p2)) + (qq1 - 2 (qq2 - q2)) + 5 (a1 - 2 a2)
+        const f2 ntp = fma2(S2(-2.0f), sub2(pp2, r2.p), pp1);
+        const f2 ntq = fma2(S2(-2.0f), sub2(qq2, r2.q), qq1);
+        const f2 a2 = add2(sub2(r0.c, r2.c), sub2(r4.c, r2.c));
+        const f2 a1 = add2(sub2(r1.c, r2.c), sub2(r3.c, r2.c));
+        const f2 nsyy = fma2(S2(5.0f), fma2(S2(-2.0f), a2, a1), add2(ntp, ntq));
+        const float nf = (float)(200.0 * p.inv_d2);  // curvature = -200 (z_xx + z_yy) / d2 = (nsxx + nsyy) * 200 / d2
+        const f2 o = fma2(add2(nsxx, nsyy), S2(nf), car);
+        store2<FAST>(p.out[3], off, full, nvalid, o.x, o.y);
+    }
+}
+
+template <bool ALG, unsigned CMASK, bool PACKED>
 __global__ void __launch_bounds__(NTHREADS, 2)
 florinsky_sliding_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TerrainParams p) {
     constexpr uint32_t STAGE_BYTES = BOXW * FL_BOXH * sizeof(float);
@@ -199,7 +330,7 @@ florinsky_sliding_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
         // interior strips (all 32 lanes write two pixels, all 15 rows exist) take the branch-free path
         const bool warp_fast = __all_sync(0xffffffffu, full) && (y_first + FL_RPW <= p.row_end);
         if (active && y_first < p.row_end) {
-            RowFeat f0, f1, f2, f3, f4;
+            typename std::conditional<PACKED, RowFeat2, RowFeat>::type f0, f1, f2, f3, f4;
             make_features(base + 0 * BOXW, f0);
             make_features(base + 1 * BOXW, f1);
             make_features(base + 2 * BOXW, f2);
@@ -218,7 +349,8 @@ florinsky_sliding_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
                     const float* rp = base + (size_t)(4 + 5 * g) * BOXW;
 #define XB_FL_STEP(NEW, A, B, C, D, E)                                   \
     make_features(rp, NEW);                                              \
-    emit_row<ALG, CMASK, true>(A, B, C, D, E, p, off, true, 2);          \
+    if constexpr (PACKED) emit_row<CMASK, true>(A, B, C, D, E, p, off, true, 2);                  \
+    else emit_row<ALG, CMASK, true>(A, B, C, D, E, p, off, true, 2);                               \
     rp += BOXW, off += p.out_ld;
                     XB_FL_RING(XB_FL_STEP)
 #undef XB_FL_STEP
@@ -230,7 +362,10 @@ florinsky_sliding_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
                     const float* rp = base + (size_t)(4 + 5 * g) * BOXW;
 #define XB_FL_STEP(NEW, A, B, C, D, E)                                                            \
     make_features(rp, NEW);                                                                       \
-    if (y < p.row_end) emit_row<ALG, CMASK, false>(A, B, C, D, E, p, off, full, nvalid);          \
+    if (y < p.row_end) {                                                                          \
+        if constexpr (PACKED) emit_row<CMASK, false>(A, B, C, D, E, p, off, full, nvalid);        \
+        else emit_row<ALG, CMASK, false>(A, B, C, D, E, p, off, full, nvalid);                    \
+    }                                                                                             \
     rp += BOXW, off += p.out_ld, ++y;
                     XB_FL_RING(XB_FL_STEP)
 #undef XB_FL_STEP
@@ -294,10 +429,15 @@ int launch_florinsky_sliding(const TerrainParams& p_in, cudaStream_t stream) {
     };
     // 2 CTAs/SM: the 5-row feature ring needs ~100 registers (a 3-CTA build spills and measured 40 % slower).
     // The two headline requests get compile-time attribute masks.
-    if (alg) return launch_one(florinsky_sliding_kernel<true, 0u>);
-    if (p.surf_mask == 15u) return launch_one(florinsky_sliding_kernel<false, 15u>);  // slope+aspect+hillshade+curvature
-    if (p.surf_mask == 11u) return launch_one(florinsky_sliding_kernel<false, 11u>);  // slope+aspect+curvature
-    return launch_one(florinsky_sliding_kernel<false, 0u>);
+    const bool packed = xb_option_florinsky_packed();
+    if (alg) return launch_one(florinsky_sliding_kernel<true, 0u, false>);
+    if (p.surf_mask == 15u)  // slope+aspect+hillshade+curvature
+        return packed ? launch_one(florinsky_sliding_kernel<false, 15u, true>)
+                      : launch_one(florinsky_sliding_kernel<false, 15u, false>);
+    if (p.surf_mask == 11u)  // slope+aspect+curvature
+        return packed ? launch_one(florinsky_sliding_kernel<false, 11u, true>)
+                      : launch_one(florinsky_sliding_kernel<false, 11u, false>);
+    return launch_one(florinsky_sliding_kernel<false, 0u, false>);
 }
 
 }  // namespace xbt
