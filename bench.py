@@ -308,6 +308,25 @@ def main() -> None:
     achieved = rows * cols * bytes_per_px / (kern_ms * 1e-3) / 1e9
     traffic = ncu_traffic_per_launch(args.fit, args.size)
 
+    # what the same traffic mix (one plane read, len(attrs) planes written, no arithmetic) reaches on this box: the
+    # write-heavy mix does not attain the COPY bandwidth the contract's `peak` is (profiles/rw_mix_microbench_*.txt)
+    stream_ceiling = None
+    if len(attrs) <= 4 and (rows * cols) % 4 == 0:
+        src = buf.reshape(-1)[: rows * cols]
+        L = _lib.lib()
+        sev0, sev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cur = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(L.xb_probe_stream(src.data_ptr(), out.data_ptr(), rows * cols, len(attrs), cur))
+        torch.cuda.synchronize()
+        sev0.record()
+        for _ in range(3):
+            _lib.check(L.xb_probe_stream(src.data_ptr(), out.data_ptr(), rows * cols, len(attrs), cur))
+        sev1.record()
+        torch.cuda.synchronize()
+        probe_gbs = rows * cols * bytes_per_px / (sev0.elapsed_time(sev1) / 3 * 1e-3) / 1e9
+        stream_ceiling = {"gbs": probe_gbs, "frac_of_ceiling": achieved / probe_gbs,
+                          "what": "xb_probe_stream: trivial kernel, same bytes read/written per pixel, streaming stores"}
+
     # ------------------------------ e2e: host buffers through the C ABI (copies inside the timed region) ----------
     e2e = None
     if not args.no_e2e:
@@ -355,7 +374,8 @@ def main() -> None:
                          "traffic": traffic, "peak_source": peak_src,
                          "kernel": ("xbt::florinsky_sliding_kernel" if args.fit == "Florinsky" and len(attrs) > 3
                                     else "xbt::terrain_fused_kernel"),
-                         "kernel_ms": kern_ms, "algorithmic_bytes_per_pixel": bytes_per_px},
+                         "kernel_ms": kern_ms, "algorithmic_bytes_per_pixel": bytes_per_px,
+                         "stream_ceiling": stream_ceiling},
             "e2e": e2e, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

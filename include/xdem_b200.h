@@ -60,6 +60,11 @@ uint64_t xb_launch_count(void);
  * 7): bit k-1 lets interior variogram tiles that span exactly k lag classes use the threshold-light sweep. */
 int xb_set_option(const char* name, int value);
 
+/* Diagnostics: the trivial streaming kernel with the terrain engine's traffic mix (reads n_floats float32 from src,
+ * writes n_planes copies to dst[n_planes * n_floats] with streaming vector stores).  bench.py times it to report the
+ * bandwidth that mix can reach on the box next to the roofline of the real kernel.  Not counted in xb_launch_count. */
+int xb_probe_stream(const void* src_dev, void* dst_dev, int64_t n_floats, int n_planes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Terrain stencil engine.
  * Replaces `_get_surface_attributes` (surfit.py:1197-1305) and `_get_windowed_indexes` (window.py:926-1002) -- and,
