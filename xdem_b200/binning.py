@@ -120,6 +120,20 @@ def _select_medians(keys: torch.Tensor, bins: torch.Tensor, n_bins: int) -> tupl
         median = lower.copy()
         even = (counts % 2 == 0) & (counts > 0)
         need_next = even & (below + last < (counts // 2 + 1))  # the upper middle value is a strictly larger key
+        # the last histogram holds every key sharing the lower middle value's upper 24 bits: the next occupied digit is
+        # the next larger key; only a value that closes its 256-key bucket needs the search pass
+        found = np.zeros(n_bins, dtype=bool)
+        upper_key = np.zeros(n_bins, dtype=np.uint32)
+        for g in np.flatnonzero(need_next):
+            nz = np.flatnonzero(h[g, digit[g] + 1:])
+            if nz.size:
+                upper_key[g] = (prefix[g] & np.uint32(0xFFFFFF00)) | np.uint32(digit[g] + 1 + nz[0])
+                found[g] = True
+        if found.any():
+            with np.errstate(invalid="ignore", over="ignore"):
+                mid = ((lower + _key_to_float(upper_key)) * np.float32(0.5)).astype(np.float32)
+            median = np.where(found, mid, median).astype(np.float32)
+        need_next = need_next & ~found
         if need_next.any():
             nxt = _u32(np.full(n_bins, 0xFFFFFFFF, dtype=np.uint32), dev)
             sel = _u32(prefix, dev)

@@ -208,6 +208,22 @@ class _NKState:
             median = lower.copy()
             even = (counts % 2 == 0) & (counts > 0)
             need_next = even & (below + last_hist < (counts // 2 + 1))  # the upper median is a strictly larger key
+            # the last pass's histogram already holds every key that shares the lower median's high bits: the next
+            # occupied digit IS the next larger key; only a lower median that closes its bucket needs a search pass
+            upper_key = np.zeros(n_groups, dtype=np.uint32)
+            found = np.zeros(n_groups, dtype=bool)
+            last_shift, last_digits = passes[-1]
+            for g in np.flatnonzero(need_next):
+                nz = np.flatnonzero(h[g, digit[g] + 1:])
+                if nz.size:
+                    d2 = int(digit[g] + 1 + nz[0])
+                    low_mask = np.uint32(((last_digits - 1) << last_shift))
+                    upper_key[g] = (prefix[g] & ~low_mask) | np.uint32(d2 << last_shift)
+                    found[g] = True
+            if found.any():
+                up = _ordered_to_float(upper_key).astype(np.float64)
+                median = np.where(found, 0.5 * (lower + up), median)
+            need_next = need_next & ~found
             if need_next.any():
                 nxt = _u32_tensor(np.full(n_groups, 0xFFFFFFFF, dtype=np.uint32), dev)
                 if mode == 0:
