@@ -77,6 +77,63 @@ def test_host_helpers() -> None:
     assert xb._stat_kind(xb.nmad) == ("nmad", "nmad")
 
 
+def _float_to_key(v: np.ndarray) -> np.ndarray:
+    u = v.astype(np.float32).view(np.uint32)
+    return np.where(u & np.uint32(0x80000000), ~u, u | np.uint32(0x80000000)).astype(np.uint32)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_radix_select_host_driver_with_numpy_passes(seed: int) -> None:
+    """The host side of the exact median (digit picking, ties, even counts, the upper middle value taken from the last
+    histogram or from a search pass, empty bins) against np.median, with NumPy stand-ins for the two kernels."""
+    from xdem_b200 import binning as xb
+
+    rng = np.random.default_rng(seed)
+    n_bins = 7
+    n = 4000
+    bins = rng.integers(0, n_bins - 1, n)  # the last bin stays empty
+    vals = rng.normal(size=n).astype(np.float32)
+    vals[rng.choice(n, 800, replace=False)] = np.round(vals[:800] * 2) / 2  # heavy ties, +-0.0
+    if seed == 1:  # a bin with two samples whose keys differ in the top digit (needs the search pass)
+        sel = np.flatnonzero(bins == 2)
+        bins[sel[2:]] = 3
+        vals[sel[0]], vals[sel[1]] = np.float32(-3.5e20), np.float32(7.25e-12)
+    if seed == 2:  # even count, neighbours in the same 256-key bucket (taken from the last histogram)
+        sel = np.flatnonzero(bins == 4)
+        bins[sel[4:]] = 0
+        vals[sel[:4]] = np.array([1.0, np.nextafter(np.float32(1.0), np.float32(2.0)), 5.0, -5.0], dtype=np.float32)
+    keys = _float_to_key(vals)
+    calls = {"hist": 0, "next": 0}
+
+    def hist_fn(prefix: np.ndarray, mask: int, shift: int) -> np.ndarray:
+        calls["hist"] += 1
+        h = np.zeros((n_bins, 256), dtype=np.int64)
+        ok = (keys & np.uint32(mask)) == prefix[bins]
+        np.add.at(h, (bins[ok], (keys[ok] >> np.uint32(shift)) & np.uint32(255)), 1)
+        return h
+
+    def next_fn(sel_keys: np.ndarray) -> np.ndarray:
+        calls["next"] += 1
+        out = np.full(n_bins, 0xFFFFFFFF, dtype=np.uint32)
+        for b in range(n_bins):
+            k = keys[(bins == b) & (keys > sel_keys[b])]
+            if k.size:
+                out[b] = k.min()
+        return out
+
+    med, cnt = xb.radix_select_medians(hist_fn, next_fn, n_bins)
+    assert calls["hist"] == 4 and calls["next"] <= 1
+    for b in range(n_bins):
+        sel = vals[bins == b]
+        assert cnt[b] == sel.size
+        if sel.size == 0:
+            assert np.isnan(med[b])
+        else:
+            assert med[b] == np.median(sel), (b, med[b], np.median(sel))  # float32 median, bit for bit
+    if seed == 1:
+        assert calls["next"] == 1
+
+
 # ---------------------------------------------------------------------------------------------------------- GPU
 
 

@@ -21,7 +21,7 @@ import torch
 
 from xdem_b200 import _arrays, _lib
 
-__all__ = ["nd_binning", "nmad", "binned_robust_stats", "bin_edges"]
+__all__ = ["nd_binning", "nmad", "binned_robust_stats", "bin_edges", "radix_select_medians"]
 
 NMAD_FACTOR = 1.4826
 
@@ -90,61 +90,79 @@ def _pick_digit(hist: np.ndarray, rank: np.ndarray, counts: np.ndarray) -> tuple
     return digit.astype(np.int64), below.astype(np.int64)
 
 
+def radix_select_medians(hist_fn: Callable[[np.ndarray, int, int], np.ndarray],
+                         next_fn: Callable[[np.ndarray], np.ndarray], n_bins: int) -> tuple[np.ndarray, np.ndarray]:
+    """Host driver of the per-bin exact median (np.nanmedian on float32 data) by MSD radix select, 4 passes of 8 bits.
+
+    ``hist_fn(prefix[n_bins] u32, prefix_mask, shift)`` returns the (n_bins, 256) histogram of digit
+    ``(key >> shift) & 255`` over the keys with ``key & prefix_mask == prefix[bin]``; ``next_fn(sel[n_bins] u32)`` returns
+    per bin the smallest key strictly above ``sel[bin]`` (0xFFFFFFFF if none).  Both are one kernel launch on the device
+    (`xb_bin_hist`, `xb_bin_next`); the CPU tests drive this function with NumPy stand-ins.  Returns (median float32
+    [n_bins], NaN for empty bins; counts int64).  The mean of the two middle values of an even count is formed in
+    float32, like NumPy does for float32 input."""
+    prefix = np.zeros(n_bins, dtype=np.uint32)
+    prefix_mask = 0
+    below = np.zeros(n_bins, dtype=np.int64)
+    counts = k_lo = last = h = digit = None
+    for ip, shift in enumerate((24, 16, 8, 0)):
+        h = np.asarray(hist_fn(prefix, prefix_mask, shift)).reshape(n_bins, 256)
+        if ip == 0:
+            counts = h.sum(axis=1)
+            k_lo = (counts - 1) // 2
+        digit, below_d = _pick_digit(h, k_lo - below, counts)
+        below += below_d
+        prefix = (prefix | (digit.astype(np.uint32) << np.uint32(shift))).astype(np.uint32)
+        prefix_mask |= 255 << shift
+        last = h[np.arange(n_bins), digit]
+    # prefix = exact key of the lower middle value; `below` keys are smaller, `last` keys are equal to it
+    lower = _key_to_float(prefix)
+    median = lower.copy()
+    even = (counts % 2 == 0) & (counts > 0)
+    need_next = even & (below + last < (counts // 2 + 1))  # the upper middle value is a strictly larger key
+    # the last histogram holds every key sharing the lower middle value's upper 24 bits: the next occupied digit is
+    # the next larger key; only a value that closes its 256-key bucket needs the search pass
+    found = np.zeros(n_bins, dtype=bool)
+    upper_key = np.zeros(n_bins, dtype=np.uint32)
+    for g in np.flatnonzero(need_next):
+        nz = np.flatnonzero(h[g, digit[g] + 1:])
+        if nz.size:
+            upper_key[g] = (prefix[g] & np.uint32(0xFFFFFF00)) | np.uint32(digit[g] + 1 + nz[0])
+            found[g] = True
+    need_next = need_next & ~found
+    if need_next.any():
+        nxt = np.asarray(next_fn(prefix)).astype(np.uint32)
+        upper_key = np.where(need_next, nxt, upper_key).astype(np.uint32)
+        found |= need_next
+    if found.any():
+        with np.errstate(invalid="ignore", over="ignore"):
+            mid = ((lower + _key_to_float(upper_key)) * np.float32(0.5)).astype(np.float32)
+        median = np.where(found, mid, median).astype(np.float32)
+    median = np.where(counts > 0, median, np.float32(np.nan)).astype(np.float32)
+    return median, counts.astype(np.int64)
+
+
 def _select_medians(keys: torch.Tensor, bins: torch.Tensor, n_bins: int) -> tuple[np.ndarray, np.ndarray]:
-    """Exact per-bin medians of float32 keys (np.nanmedian on float32 data: the mean of the two middle values of an even
-    count is formed in float32).  Returns (median float32 [n_bins] with NaN for empty bins, counts int64)."""
+    """`radix_select_medians` with the histogram / next-key passes running as CUDA kernels over (keys, bins)."""
     L = _lib.lib()
     dev = keys.device
     n = int(keys.numel())
     stream = torch.cuda.current_stream(dev).cuda_stream
-    prefix = np.zeros(n_bins, dtype=np.uint32)
-    prefix_mask = 0
-    below = np.zeros(n_bins, dtype=np.int64)
-    counts = k_lo = last = None
+
+    def hist_fn(prefix: np.ndarray, prefix_mask: int, shift: int) -> np.ndarray:
+        hist = torch.zeros(n_bins * 256, dtype=torch.int64, device=dev)
+        pre = _u32(prefix, dev)
+        _lib.check(L.xb_bin_hist(keys.data_ptr(), bins.data_ptr(), n, n_bins, pre.data_ptr(), prefix_mask, shift,
+                                 hist.data_ptr(), stream))
+        return hist.cpu().numpy()
+
+    def next_fn(sel: np.ndarray) -> np.ndarray:
+        nxt = _u32(np.full(n_bins, 0xFFFFFFFF, dtype=np.uint32), dev)
+        sel_t = _u32(sel, dev)
+        _lib.check(L.xb_bin_next(keys.data_ptr(), bins.data_ptr(), n, n_bins, sel_t.data_ptr(), nxt.data_ptr(), stream))
+        return nxt.cpu().numpy().view(np.uint32)
+
     with torch.cuda.device(dev):
-        for ip, shift in enumerate((24, 16, 8, 0)):
-            hist = torch.zeros(n_bins * 256, dtype=torch.int64, device=dev)
-            pre = _u32(prefix, dev)
-            _lib.check(L.xb_bin_hist(keys.data_ptr(), bins.data_ptr(), n, n_bins, pre.data_ptr(), prefix_mask, shift,
-                                     hist.data_ptr(), stream))
-            h = hist.cpu().numpy().reshape(n_bins, 256)
-            if ip == 0:
-                counts = h.sum(axis=1)
-                k_lo = (counts - 1) // 2
-            digit, below_d = _pick_digit(h, k_lo - below, counts)
-            below += below_d
-            prefix = (prefix | (digit.astype(np.uint32) << np.uint32(shift))).astype(np.uint32)
-            prefix_mask |= 255 << shift
-            last = h[np.arange(n_bins), digit]
-        lower = _key_to_float(prefix)
-        median = lower.copy()
-        even = (counts % 2 == 0) & (counts > 0)
-        need_next = even & (below + last < (counts // 2 + 1))  # the upper middle value is a strictly larger key
-        # the last histogram holds every key sharing the lower middle value's upper 24 bits: the next occupied digit is
-        # the next larger key; only a value that closes its 256-key bucket needs the search pass
-        found = np.zeros(n_bins, dtype=bool)
-        upper_key = np.zeros(n_bins, dtype=np.uint32)
-        for g in np.flatnonzero(need_next):
-            nz = np.flatnonzero(h[g, digit[g] + 1:])
-            if nz.size:
-                upper_key[g] = (prefix[g] & np.uint32(0xFFFFFF00)) | np.uint32(digit[g] + 1 + nz[0])
-                found[g] = True
-        if found.any():
-            with np.errstate(invalid="ignore", over="ignore"):
-                mid = ((lower + _key_to_float(upper_key)) * np.float32(0.5)).astype(np.float32)
-            median = np.where(found, mid, median).astype(np.float32)
-        need_next = need_next & ~found
-        if need_next.any():
-            nxt = _u32(np.full(n_bins, 0xFFFFFFFF, dtype=np.uint32), dev)
-            sel = _u32(prefix, dev)
-            _lib.check(L.xb_bin_next(keys.data_ptr(), bins.data_ptr(), n, n_bins, sel.data_ptr(), nxt.data_ptr(),
-                                     stream))
-            upper = _key_to_float(nxt.cpu().numpy().view(np.uint32))
-            with np.errstate(invalid="ignore", over="ignore"):
-                mid = ((lower + upper) * np.float32(0.5)).astype(np.float32)  # float32 mean of the two middles
-            median = np.where(need_next, mid, median).astype(np.float32)
-    median = np.where(counts > 0, median, np.float32(np.nan)).astype(np.float32)
-    return median, counts.astype(np.int64)
+        return radix_select_medians(hist_fn, next_fn, n_bins)
 
 
 def binned_robust_stats(values: torch.Tensor, variables: list[torch.Tensor], edges: list[np.ndarray],
