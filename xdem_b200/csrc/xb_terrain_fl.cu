@@ -17,6 +17,11 @@
 // per pixel for the same four derivatives.  Same tiles, TMA staging, NaN rule, attribute math and outputs as the generic
 // kernel; results are identical up to the association order of exact sums (tested bit-for-bit on integer DEMs and to
 // <= 1e-6 relative against the generic kernel / reference fixtures).
+//
+// Three specialisations on top of that (each A/B-measured): compile-time attribute masks for the two
+// headline requests, a warp-uniform branch-free path for interior strips, and packed f32x2 arithmetic (FADD2 / FMUL2 /
+// FFMA2) for the two pixels of a lane -- 126 -> 78 issue slots per pixel; the kernel now runs at 0.94 of the bandwidth
+// a no-arithmetic kernel with the same read/write mix reaches.
 #include <stdlib.h>
 
 #include <type_traits>
