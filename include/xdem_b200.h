@@ -56,7 +56,8 @@ int xb_version(void);
 /* Number of kernels this library launched since load (all entry points); bench.py reports it as gpu_launches. */
 uint64_t xb_launch_count(void);
 /* Tuning / test knobs.  "florinsky_generic" = 1 routes Florinsky requests through the generic fused kernel instead of
- * the row-feature-reuse kernel (both are parity-tested; used for A/B checks).  "variogram_full_tiles" = bit mask (default
+ * the row-feature-reuse kernel (both are parity-tested; used for A/B checks); "window3_generic" = 1 does the same for the
+ * 3x3 windowed indexes (generic fused kernel instead of xb_terrain_w3.cu).  "variogram_full_tiles" = bit mask (default
  * 7): bit k-1 lets interior variogram tiles that span exactly k lag classes use the threshold-light sweep. */
 int xb_set_option(const char* name, int value);
 
@@ -64,6 +65,12 @@ int xb_set_option(const char* name, int value);
  * writes n_planes copies to dst[n_planes * n_floats] with streaming vector stores).  bench.py times it to report the
  * bandwidth that mix can reach on the box next to the roofline of the real kernel.  Not counted in xb_launch_count. */
 int xb_probe_stream(const void* src_dev, void* dst_dev, int64_t n_floats, int n_planes, void* stream);
+/* Diagnostics: bit-exactness of the branch-free IEEE cores of the 3x3 windowed kernel against the CUDA round-to-nearest
+ * intrinsics, over `count` consecutive float32 bit patterns x starting at bits_begin.  kind 0: the fast-path square root
+ * vs __fsqrt_rn(x) (valid range [2^-101, FLT_MAX]); kind 1: the reciprocal-multiply division x / b (rcp_b = RN(1/b)) vs
+ * __fdiv_rn(x, b).  The number of differing results is added to mismatches_dev[0]. */
+int xb_probe_exact_math(int kind, uint32_t bits_begin, uint64_t count, float b, float rcp_b,
+                        unsigned long long* mismatches_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Terrain stencil engine.

@@ -434,3 +434,73 @@ def test_florinsky_sliding_kernel_vs_generic_and_oracle(xb, shape) -> None:
             ref = to.get_terrain_attribute(d, attrs, resolution=5.0)
             for i, name in enumerate(attrs):
                 parity.assert_attr_close(a[i], ref[i], name, where=keep, msg=f"sliding vs oracle {shape}")
+
+
+def test_exact_math_cores(xb) -> None:
+    """The branch-free IEEE cores of the 3x3 windowed kernel (xb_terrain_w3.cu) against the CUDA round-to-nearest
+    intrinsics, bit for bit: the fast-path square root over EVERY float32 of its range [2^-101, FLT_MAX], and the
+    reciprocal-multiply division by L^2 for the resolutions used in the tests over every positive normal float32
+    whose quotient stays normal."""
+    import ctypes
+
+    import torch
+
+    from xdem_b200 import _lib
+
+    L = _lib.lib()
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    lo, hi = 0x0D000000, 0x7F7FFFFF
+    _lib.check(L.xb_probe_exact_math(0, lo, hi - lo + 1, 1.0, 1.0, bad.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0, f"fast sqrt differs from __fsqrt_rn on {int(bad.item())} inputs"
+    for res in (5.0, 1.0, 30.0, 0.5, 2.5, 0.1, 100.0, 3.0, 1e-3, 12345.678):
+        ll = np.float32(res * res)
+        cands = [np.nextafter(np.float32(1.0 / np.float64(ll)), np.float32(d)) for d in (0.0, np.inf)]
+        cands.append(np.float32(1.0 / np.float64(ll)))
+        y = min(cands, key=lambda c: abs(np.float64(ll) * np.float64(c) - 1.0))
+        bad.zero_()
+        # numerators 2^-40 .. 2^60: every bit pattern in between (areas are ~L^2)
+        lo, hi = 0x2B800000, 0x5D800000
+        _lib.check(L.xb_probe_exact_math(1, lo, hi - lo + 1, ctypes.c_float(float(ll)), ctypes.c_float(float(y)),
+                                         bad.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert int(bad.item()) == 0, f"division by {ll} differs from __fdiv_rn on {int(bad.item())} inputs"
+
+
+@pytest.mark.parametrize("res", [5.0, 1.0, 30.0, 0.37, 1e-7])
+@pytest.mark.parametrize("tm", ["Riley", "Wilson"])
+def test_window3_sliding_equals_generic(xb, res: float, tm: str) -> None:
+    """The row-feature-reuse 3x3 kernel (packed f32x2, shared Jenness segments, fast IEEE sqrt / division) is
+    bit-identical to the generic fused kernel on rough data with NaN / inf cells, ragged widths and for every subset
+    mask; a resolution outside the fast cores' range (1e-7) must fall back to the generic kernel by itself."""
+    import torch
+
+    from xdem_b200 import _engine, _lib
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    H, W = 701, 1028  # width multiple of 4 (TMA eligible) but not of the tile; ragged rows
+    z = 1000 + 30 * torch.randn((H, W), generator=g, device="cuda")
+    z[::97, ::53] = float("nan")
+    z[300, 400] = float("inf")
+    z[500:520, 600:640] = 123.0  # flat patch: TRI = 0 exactly
+    for attrs in (WIN, WIN[:3], ["rugosity"], ["roughness", "rugosity"], ["terrain_ruggedness_index"]):
+        fast = _engine.terrain_fused(z, res, windowed_indexes=attrs, tri_method=tm)
+        _lib.set_option("window3_generic", 1)
+        try:
+            ref = _engine.terrain_fused(z, res, windowed_indexes=attrs, tri_method=tm)
+        finally:
+            _lib.set_option("window3_generic", 0)
+        assert torch.equal(torch.isnan(fast), torch.isnan(ref)), attrs
+        assert torch.equal(fast.view(torch.int32), ref.view(torch.int32)), (attrs, res, tm)
+
+
+def test_all13_split_equals_separate(xb, G) -> None:
+    """BASELINE config 4's request (9 surface attributes + 4 windowed indexes, Florinsky) runs as two specialised
+    launches; the planes must equal the ones of separate requests bit for bit."""
+    dem = G["in|fractal"]
+    surf = [a for a in SURF if a != "curvature"]
+    outs = xb.terrain.get_terrain_attribute(dem, surf + WIN, resolution=5.0)
+    so = xb.terrain.get_terrain_attribute(dem, surf, resolution=5.0)
+    wo = xb.terrain.get_terrain_attribute(dem, WIN, resolution=5.0)
+    for a, o, r in zip(surf + WIN, outs, list(so) + list(wo)):
+        assert np.array_equal(o, r, equal_nan=True), a

@@ -25,6 +25,8 @@ static std::atomic<int> g_opt_fl_generic{0};
 bool xb_option_florinsky_generic() { return g_opt_fl_generic.load() != 0; }
 static std::atomic<int> g_opt_fl_packed{1};
 bool xb_option_florinsky_packed() { return g_opt_fl_packed.load() != 0; }
+static std::atomic<int> g_opt_w3_generic{0};
+bool xb_option_window3_generic() { return g_opt_w3_generic.load() != 0; }
 static std::atomic<int> g_opt_vg_full{7};
 int xb_option_variogram_full_tiles() { return g_opt_vg_full.load(); }
 
@@ -119,6 +121,8 @@ int xb_build_terrain_params(xbt::TerrainParams& p, int dtype, double resolution,
     } else {
         p.inv_d1 = 1.0 / (420 * r), p.inv_d2 = 1.0 / (35 * r * r), p.inv_d3 = 1.0 / (100 * r * r);
     }
+    p.alg_k3 = p.inv_d2 != 0.0 ? p.inv_d3 / p.inv_d2 : 0.0;
+    p.alg_c2 = 100.0 * p.inv_d2;
     // np.rad2deg on a float32 array multiplies by the float32 constant 180.0f/pi_f (terrain.py:591)
     p.rad2deg = dtype == XB_F32 ? (double)(180.0f / 3.14159265358979323846f) : 180.0 / M_PI;
     // surfit.py:614-615
@@ -135,12 +139,39 @@ int xb_build_terrain_params(xbt::TerrainParams& p, int dtype, double resolution,
         p.rug_dl2_diag = (double)(diag * diag);
         p.rug_dl2_straight = (double)(L * L);
         p.rug_ll = (double)(float)(r * r);
+        // RN(1 / L^2) in float32: the candidate nearest to the double quotient or one of its neighbours, whichever
+        // minimises |L^2 y - 1| (the product of two float32 values is exact in double)
+        const float ll = (float)p.rug_ll;
+        float y = (float)(1.0 / (double)ll);
+        const float cand[3] = {nextafterf(y, 0.0f), y, nextafterf(y, INFINITY)};
+        double best = INFINITY;
+        for (float cnd : cand) {
+            const double e = fabs((double)ll * (double)cnd - 1.0);
+            if (e < best) best = e, y = cnd;
+        }
+        p.rug_rcp_ll = (double)y;
+        // Markstein's correctly rounded a/b needs a mantissa of b that is not all ones
+        uint32_t llbits;
+        memcpy(&llbits, &ll, 4);
+        p.rug_fast_ok = (r >= 1e-6 && r <= 1e8 && (llbits & 0x7fffffu) != 0x7fffffu) ? 1 : 0;
     } else {
         const double diag = sqrt(2.0) * r;
         p.rug_dl2_diag = diag * diag;
         p.rug_dl2_straight = r * r;
         p.rug_ll = r * r;
     }
+    p.f.inv1 = (float)p.inv_d1;
+    p.f.ang = p.degrees ? (float)p.rad2deg : 1.0f;
+    p.f.hs_ky = (float)p.hs_ky;
+    p.f.hs_nkx = -(float)p.hs_kx;
+    p.f.hs_sa = (float)p.hs_sin_alt;
+    p.f.zf2 = (float)p.zf2;
+    p.f.curv_nf = (float)(200.0 * p.inv_d2);
+    p.f.alg_c2 = (float)p.alg_c2;
+    p.f.rug_rcp_ll = (float)p.rug_rcp_ll;
+    p.f.rug_nll = -(float)p.rug_ll;
+    p.f.rug_l2s = (float)p.rug_dl2_straight;
+    p.f.rug_l2d = (float)p.rug_dl2_diag;
     *hs_out = hs;
     *hw_out = hw;
     return XB_OK;
@@ -161,6 +192,10 @@ int xb_set_option(const char* name, int value) {
     }
     if (name && strcmp(name, "florinsky_packed") == 0) {
         g_opt_fl_packed.store(value);
+        return XB_OK;
+    }
+    if (name && strcmp(name, "window3_generic") == 0) {
+        g_opt_w3_generic.store(value);
         return XB_OK;
     }
     if (name && strcmp(name, "variogram_full_tiles") == 0) {

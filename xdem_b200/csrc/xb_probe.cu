@@ -4,7 +4,7 @@
 // (write-heavy traffic does not reach the copy bandwidth of MEASURED_PEAKS.json).  Diagnostics only.
 #include "../../include/xdem_b200.h"
 
-#include "xb_common.cuh"
+#include "xb_terrain_dev.cuh"
 
 void xb_count_launch(int n);
 
@@ -18,6 +18,30 @@ stream_kernel(const float4* __restrict__ src, float4* __restrict__ dst, size_t n
 #pragma unroll
         for (int p = 0; p < NP; ++p) __stcs(dst + (size_t)p * n4 + i, make_float4(v.x + (float)p, v.y, v.z, v.w));
     }
+}
+
+// Bit-exactness probes of the branch-free IEEE cores used by the 3x3 windowed kernel (xb_terrain_w3.cu).
+// kind 0: sqrt2_rn_fast(x) vs __fsqrt_rn(x);  kind 1: div2_rn_const(x, y, -b) vs __fdiv_rn(x, b);
+// x runs over the `count` consecutive float32 bit patterns starting at bits_begin.
+__global__ void __launch_bounds__(256)
+exact_math_kernel(int kind, uint32_t bits_begin, unsigned long long count, float b, float y,
+                  unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; 2 * i < count;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t b0 = bits_begin + (uint32_t)(2 * i), b1 = (2 * i + 1 < count) ? b0 + 1 : b0;
+        const float2 x = make_float2(__uint_as_float(b0), __uint_as_float(b1));
+        float2 fast, ref;
+        if (kind == 0) {
+            fast = xbt::sqrt2_rn_fast(x);
+            ref = make_float2(__fsqrt_rn(x.x), __fsqrt_rn(x.y));
+        } else {
+            fast = xbt::div2_rn_const(x, y, -b);
+            ref = make_float2(__fdiv_rn(x.x, b), __fdiv_rn(x.y, b));
+        }
+        bad += (__float_as_uint(fast.x) != __float_as_uint(ref.x)) + (__float_as_uint(fast.y) != __float_as_uint(ref.y));
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 }  // namespace xbp
@@ -45,6 +69,21 @@ int xb_probe_stream(const void* src_dev, void* dst_dev, int64_t n_floats, int n_
         case 3: xbp::stream_kernel<3><<<grid, 256, 0, st>>>(s, d, n4); break;
         default: xbp::stream_kernel<4><<<grid, 256, 0, st>>>(s, d, n4); break;
     }
+    XB_CUDA_CHECK(cudaGetLastError());
+    return XB_OK;
+}
+
+int xb_probe_exact_math(int kind, uint32_t bits_begin, uint64_t count, float b, float rcp_b,
+                        unsigned long long* mismatches_dev, void* stream) {
+    if ((kind != 0 && kind != 1) || !mismatches_dev || count == 0) {
+        xb_set_error("bad arguments to xb_probe_exact_math");
+        return XB_ERR_INVALID;
+    }
+    int sms = 0;
+    int rc = xb_num_sms(&sms);
+    if (rc) return rc;
+    xbp::exact_math_kernel<<<sms * 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        kind, bits_begin, (unsigned long long)count, b, rcp_b, mismatches_dev);
     XB_CUDA_CHECK(cudaGetLastError());
     return XB_OK;
 }

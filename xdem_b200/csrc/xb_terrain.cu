@@ -311,7 +311,7 @@ terrain_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             T r6[6];
-                            curv_alg<T>(sx[k], sy[k], sxx[k], syy[k], sxy[k], p, r6);
+                            curv_alg<T>(sx[k], sy[k], sxx[k], syy[k], sxy[k], p, smask, r6);
                             o4[k] = r6[0] + car[k], o5[k] = r6[1] + car[k], o6[k] = r6[2] + car[k];
                             o7[k] = r6[3] + car[k], o8[k] = r6[4] + car[k], o9[k] = r6[5] + car[k];
                         }
@@ -554,12 +554,32 @@ int launch(const TerrainParams& p_in, int dtype, int hs, int hw, cudaStream_t st
     // TMA needs a 16-byte aligned base and pitch; otherwise the cooperative loader variant runs
     bool use_tma = (reinterpret_cast<uintptr_t>(p.dem) % 16 == 0) && ((p.ld * es) % 16 == 0) &&
                    p.cols < (1ll << 31) && p.rows_buf < (1ll << 31);
+    // float32 requests that mix surface attributes with 3x3 windowed indexes (e.g. "all attributes", BASELINE config 4)
+    // run as two specialised launches: the second read of the DEM (4 B/px of 60) costs far less than the combined
+    // generic kernel loses to register pressure (r02base: all 13 planes 8.37 ms at 16384^2 vs 3.35 + 4.19 ms apart).
+    if (use_tma && dtype == 0 && hs > 0 && hw == 1 && xb_get_tensormap_encoder()) {
+        TerrainParams ps = p, pw = p;
+        ps.win_mask = 0;
+        pw.surf_mask = 0;
+        for (int i = 10; i < 14; ++i) ps.out[i] = nullptr;
+        for (int i = 0; i < 10; ++i) pw.out[i] = nullptr;
+        const int rc = launch(ps, dtype, hs, 0, stream);
+        if (rc) return rc;
+        return launch(pw, dtype, 0, hw, stream);
+    }
+    // float32 3x3 windowed indexes: the row-feature-reuse kernel (xb_terrain_w3.cu) shares the Jenness segments between
+    // neighbouring pixels and uses packed f32x2 arithmetic.  xb_set_option("window3_generic", 1) forces the generic
+    // kernel (A/B tests).
+    if (use_tma && dtype == 0 && hs == 0 && hw == 1 && !xb_option_window3_generic() && xb_get_tensormap_encoder() &&
+        (!(p.win_mask & 8u) || p.rug_fast_ok))
+        return launch_window3_sliding(p, stream);
     // float32 Florinsky with second-derivative attributes: the row-feature-reuse kernel (xb_terrain_fl.cu) is ~25 %
     // faster (ncu/A-B: 1.42 vs 1.86 ms at 16384^2 for slope+aspect+hillshade+curvature); first-derivative-only requests
     // stay on the generic kernel, which computes just z_x, z_y at higher occupancy.  xb_set_option("florinsky_generic",1)
     // forces the generic kernel (A/B tests).
-    if (use_tma && dtype == 0 && hs == 2 && hw == 0 && p.fit_id == XB_FIT_FLORINSKY_ID && (p.surf_mask & ~7u) != 0 &&
-        !xb_option_florinsky_generic() && xb_get_tensormap_encoder())
+    if (use_tma && dtype == 0 && hs == 2 && hw == 0 && p.fit_id == XB_FIT_FLORINSKY_ID &&
+        !xb_option_florinsky_generic() && xb_get_tensormap_encoder() &&
+        ((p.surf_mask & ~7u) != 0 || (xb_option_florinsky_packed() && florinsky_has_packed_mask(p.surf_mask))))
         return launch_florinsky_sliding(p, stream);
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));

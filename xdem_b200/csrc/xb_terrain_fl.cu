@@ -56,17 +56,6 @@ __device__ __forceinline__ void make_features(const float* row, RowFeat& f) {
     }
 }
 
-template <bool FAST>
-__device__ __forceinline__ void store2(void* plane, long long off, bool full, int nvalid, float v0, float v1) {
-    float* p = reinterpret_cast<float*>(plane) + off;
-    if (FAST || full) {
-        __stcs(reinterpret_cast<float2*>(p), make_float2(v0, v1));
-    } else {
-        if (nvalid > 0) __stcs(p, v0);
-        if (nvalid > 1) __stcs(p + 1, v1);
-    }
-}
-
 // rows r = -2..2 of the current output row are ring slots S0..S4
 // CMASK != 0: the surface-attribute mask is a compile-time constant (common requests), which turns the attribute blocks
 // into one straight-line region the scheduler can interleave; CMASK == 0: runtime mask.
@@ -112,20 +101,20 @@ __device__ __forceinline__ void emit_row(const RowFeat& r0, const RowFeat& r1, c
     }
     if (need_sah) {
         float zx[2], zy[2], g2[2];
-        const float inv1 = (float)p.inv_d1;
+        const float inv1 = p.f.inv1;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             zx[k] = sx[k] * inv1, zy[k] = sy[k] * inv1;
             g2[k] = fmaf(zx[k], zx[k], zy[k] * zy[k]);
         }
-        const float ang = p.degrees ? (float)p.rad2deg : 1.0f;
+        const float ang = p.f.ang;
         if (mask & 1u)
             store2<FAST>(p.out[0], off, full, nvalid, slope_rad(g2[0]) * ang + car[0], slope_rad(g2[1]) * ang + car[1]);
         if (mask & 2u)
             store2<FAST>(p.out[1], off, full, nvalid, aspect_rad(zx[0], zy[0]) * ang + car[0],
                    aspect_rad(zx[1], zy[1]) * ang + car[1]);
         if (mask & 4u) {
-            const float ky = (float)p.hs_ky, kx = -(float)p.hs_kx, sa = (float)p.hs_sin_alt, zf2 = (float)p.zf2;
+            const float ky = p.f.hs_ky, kx = p.f.hs_nkx, sa = p.f.hs_sa, zf2 = p.f.zf2;
             const float lo = p.clip_hs ? 0.0f : -CUDART_INF_F, hi = p.clip_hs ? 255.0f : CUDART_INF_F;
             float o[2];
 #pragma unroll
@@ -138,14 +127,14 @@ __device__ __forceinline__ void emit_row(const RowFeat& r0, const RowFeat& r1, c
         }
     }
     if (mask & 8u) {
-        const float f = (float)(-200.0 * p.inv_d2);
+        const float f = -p.f.curv_nf;
         store2<FAST>(p.out[3], off, full, nvalid, (sxx[0] + syy[0]) * f + car[0], (sxx[1] + syy[1]) * f + car[1]);
     }
     if constexpr (ALG) {
         if (mask & ~15u) {
             float r6a[6], r6b[6];
-            curv_alg<float>(sx[0], sy[0], sxx[0], syy[0], sxy[0], p, r6a);
-            curv_alg<float>(sx[1], sy[1], sxx[1], syy[1], sxy[1], p, r6b);
+            curv_alg<float>(sx[0], sy[0], sxx[0], syy[0], sxy[0], p, mask, r6a);
+            curv_alg<float>(sx[1], sy[1], sxx[1], syy[1], sxy[1], p, mask, r6b);
 #pragma unroll
             for (int a = 0; a < 6; ++a)
                 if (mask & (1u << (4 + a)))
@@ -162,12 +151,6 @@ __device__ __forceinline__ void emit_row(const RowFeat& r0, const RowFeat& r1, c
 // negated (nsxx = -z_xx sums, nsyy) so that every subtraction is a single FFMA2 with a -1 / -2 constant (packed ops have
 // no operand-negate modifier).  MUFU seeds, min/max and the quadrant selects stay scalar.
 // ---------------------------------------------------------------------------------------------------------------
-using f2 = float2;
-__device__ __forceinline__ f2 S2(float s) { return make_float2(s, s); }
-__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return __ffma2_rn(b, S2(-1.0f), a); }  // a - b, one rounding
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
 
 struct RowFeat2 {
     f2 p, q, D, E, c;
@@ -204,7 +187,9 @@ template <unsigned CMASK, bool FAST>
 __device__ __forceinline__ void emit_row(const RowFeat2& r0, const RowFeat2& r1, const RowFeat2& r2, const RowFeat2& r3,
                                          const RowFeat2& r4, const TerrainParams& p, long long off, bool full,
                                          int nvalid) {
-    static_assert(CMASK != 0 && (CMASK & ~15u) == 0, "packed path: compile-time mask without the curvature algebra");
+    static_assert(CMASK != 0, "packed path: compile-time attribute mask");
+    constexpr bool NEED2 = (CMASK & ~7u) != 0;    // any second-derivative attribute
+    constexpr bool NEEDALG = (CMASK & ~15u) != 0;  // curvature algebra (per-pixel FP64 numerators, curv_alg<float>)
     // z_x (fl_p, divider 420 res)
     f2 sx = mul2(S2(31.0f), add2(r0.D, r4.D));
     sx = fma2(S2(-5.0f), add2(r1.D, r3.D), sx);
@@ -217,16 +202,22 @@ __device__ __forceinline__ void emit_row(const RowFeat2& r0, const RowFeat2& r1,
     const f2 t2 = fma2(S2(62.0f), sub2(r3.q, r1.q), mul2(S2(44.0f), sub2(r3.p, r1.p)));
     const f2 t3 = fma2(S2(280.0f), sub2(r3.c, r1.c), mul2(S2(35.0f), sub2(r0.c, r4.c)));
     const f2 sy = add2(add2(t1, t2), t3);
-    const f2 pp2 = add2(r0.p, r4.p), pp1 = add2(r1.p, r3.p);
-    const f2 qq2 = add2(r0.q, r4.q), qq1 = add2(r1.q, r3.q);
-    const f2 sp = add2(add2(pp2, pp1), r2.p), sq = add2(add2(qq2, qq1), r2.q);
-    const f2 nsxx = fma2(S2(-2.0f), sp, sq);  // -(2 sp - sq): touches every cell of the window
-    const f2 car = mul2(nsxx, S2(0.0f));
+    f2 pp2, pp1, qq2, qq1, nsxx, car;
+    if constexpr (NEED2) {
+        pp2 = add2(r0.p, r4.p), pp1 = add2(r1.p, r3.p);
+        qq2 = add2(r0.q, r4.q), qq1 = add2(r1.q, r3.q);
+        const f2 sp = add2(add2(pp2, pp1), r2.p), sq = add2(add2(qq2, qq1), r2.q);
+        nsxx = fma2(S2(-2.0f), sp, sq);  // -(2 sp - sq): touches every cell of the window
+        car = mul2(nsxx, S2(0.0f));
+    } else {
+        // first-derivative requests: z_x touches every column but the centre one, z_y every row but the centre one
+        car = mul2(add2(add2(sx, sy), r2.c), S2(0.0f));
+    }
     if (CMASK & 7u) {
-        const float inv1 = (float)p.inv_d1;
+        const float inv1 = p.f.inv1;
         const f2 zx = mul2(sx, S2(inv1)), zy = mul2(sy, S2(inv1));
         const f2 g2 = fma2(zx, zx, mul2(zy, zy));
-        const float ang = p.degrees ? (float)p.rad2deg : 1.0f;
+        const float ang = p.f.ang;
         if (CMASK & 1u) {
             // sqrt_fast on both components: r = rsqrt(max(x, tiny)); g = x r; g += (0.5 r)(x - g g)
             const f2 r = make_float2(xbm::rsqrt_approx(fmaxf(g2.x, 1.17549435e-38f)),
@@ -259,7 +250,7 @@ __device__ __forceinline__ void emit_row(const RowFeat2& r0, const RowFeat2& r1,
             store2<FAST>(p.out[1], off, full, nvalid, o.x, o.y);
         }
         if (CMASK & 4u) {
-            const float ky = (float)p.hs_ky, kx = -(float)p.hs_kx, sa = (float)p.hs_sin_alt, zf2 = (float)p.zf2;
+            const float ky = p.f.hs_ky, kx = p.f.hs_nkx, sa = p.f.hs_sa, zf2 = p.f.zf2;
             const float lo = p.clip_hs ? 0.0f : -CUDART_INF_F, hi = p.clip_hs ? 255.0f : CUDART_INF_F;
             const f2 den = fma2(S2(zf2), g2, S2(1.0f));
             const f2 r = make_float2(xb_rsqrt(den.x), xb_rsqrt(den.y));
@@ -270,16 +261,30 @@ __device__ __forceinline__ void emit_row(const RowFeat2& r0, const RowFeat2& r1,
             store2<FAST>(p.out[2], off, full, nvalid, o.x, o.y);
         }
     }
-    if (CMASK & 8u) {
+    if constexpr (NEED2) {
         // -z_yy sums: (pp1 - 2 (pp2 - p2)) + (qq1 - 2 (qq2 - q2)) + 5 (a1 - 2 a2)
         const f2 ntp = fma2(S2(-2.0f), sub2(pp2, r2.p), pp1);
         const f2 ntq = fma2(S2(-2.0f), sub2(qq2, r2.q), qq1);
         const f2 a2 = add2(sub2(r0.c, r2.c), sub2(r4.c, r2.c));
         const f2 a1 = add2(sub2(r1.c, r2.c), sub2(r3.c, r2.c));
         const f2 nsyy = fma2(S2(5.0f), fma2(S2(-2.0f), a2, a1), add2(ntp, ntq));
-        const float nf = (float)(200.0 * p.inv_d2);  // curvature = -200 (z_xx + z_yy) / d2 = (nsxx + nsyy) * 200 / d2
-        const f2 o = fma2(add2(nsxx, nsyy), S2(nf), car);
-        store2<FAST>(p.out[3], off, full, nvalid, o.x, o.y);
+        if (CMASK & 8u) {
+            const float nf = p.f.curv_nf;  // curvature = -200 (z_xx + z_yy) / d2 = (nsxx + nsyy) 200 / d2
+            const f2 o = fma2(add2(nsxx, nsyy), S2(nf), car);
+            store2<FAST>(p.out[3], off, full, nvalid, o.x, o.y);
+        }
+        if constexpr (NEEDALG) {
+            // -z_xy sums (fl_s, 100 res^2): M11 + 2 (M12 + M21) + 4 M22, mixed second differences of D / E
+            const f2 m11 = sub2(r1.E, r3.E), m12 = sub2(r3.D, r1.D), m21 = sub2(r0.E, r4.E), m22 = sub2(r4.D, r0.D);
+            const f2 nsxy = fma2(S2(4.0f), m22, fma2(S2(2.0f), add2(m12, m21), m11));
+            float r6a[6], r6b[6];
+            curv_alg<float>(sx.x, sy.x, -nsxx.x, -nsyy.x, -nsxy.x, p, CMASK, r6a);
+            curv_alg<float>(sx.y, sy.y, -nsxx.y, -nsyy.y, -nsxy.y, p, CMASK, r6b);
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+                if (CMASK & (1u << (4 + a)))
+                    store2<FAST>(p.out[4 + a], off, full, nvalid, r6a[a] + car.x, r6b[a] + car.y);
+        }
     }
 }
 
@@ -434,14 +439,23 @@ int launch_florinsky_sliding(const TerrainParams& p_in, cudaStream_t stream) {
     };
     // 2 CTAs/SM: the 5-row feature ring needs ~100 registers (a 3-CTA build spills and measured 40 % slower).
     // The two headline requests get compile-time attribute masks.
+    // Packed (f32x2) kernels with compile-time masks for the common requests: the API default DEM.slope() / aspect /
+    // hillshade and their combinations (first derivatives only), the two headline requests, curvature, and the
+    // "all attributes" request of BASELINE config 4 (nine planes, with and without the deprecated `curvature`).
     const bool packed = xb_option_florinsky_packed();
+    if (packed) {
+        switch (p.surf_mask) {
+#define XB_FL_CASE(M) \
+    case M: return launch_one(florinsky_sliding_kernel<((M) & ~15u) != 0, M, true>);
+            XB_FL_CASE(1u) XB_FL_CASE(2u) XB_FL_CASE(3u) XB_FL_CASE(4u) XB_FL_CASE(7u) XB_FL_CASE(8u) XB_FL_CASE(11u)
+            XB_FL_CASE(15u) XB_FL_CASE(0x3F7u) XB_FL_CASE(0x3FFu)
+#undef XB_FL_CASE
+            default: break;
+        }
+    }
     if (alg) return launch_one(florinsky_sliding_kernel<true, 0u, false>);
-    if (p.surf_mask == 15u)  // slope+aspect+hillshade+curvature
-        return packed ? launch_one(florinsky_sliding_kernel<false, 15u, true>)
-                      : launch_one(florinsky_sliding_kernel<false, 15u, false>);
-    if (p.surf_mask == 11u)  // slope+aspect+curvature
-        return packed ? launch_one(florinsky_sliding_kernel<false, 11u, true>)
-                      : launch_one(florinsky_sliding_kernel<false, 11u, false>);
+    if (p.surf_mask == 15u) return launch_one(florinsky_sliding_kernel<false, 15u, false>);
+    if (p.surf_mask == 11u) return launch_one(florinsky_sliding_kernel<false, 11u, false>);
     return launch_one(florinsky_sliding_kernel<false, 0u, false>);
 }
 
