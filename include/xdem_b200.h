@@ -95,15 +95,27 @@ int xb_terrain_fused(const void* dem_dev, int dtype, int64_t rows_buf, int64_t c
                      double hillshade_azimuth, double hillshade_altitude, double hillshade_z_factor,
                      void* const* out_planes_host, int64_t out_ld, void* stream);
 
-/* Same computation from/to HOST buffers (pinned memory recommended): the raster is streamed through the GPU in row
- * blocks with `depth` halo rows (the reference's tiling analogue: geoutils.map_overlap_multiproc_save,
- * terrain.py:412-466), H2D / kernel / D2H overlapped on three streams.  This is the call the `e2e` benchmark figure
- * times.  out_planes_host[i] are HOST pointers here; rows_per_block <= 0 picks ~96 MiB blocks. */
+/* Same computation from/to HOST buffers: the raster is streamed through the GPU in row blocks with `depth` halo rows
+ * (the reference's tiling analogue: geoutils.map_overlap_multiproc_save, terrain.py:412-466), H2D / kernel / D2H
+ * overlapped on three streams.  This is the call the reference-facing seam and the `e2e` benchmark figure go through.
+ * out_planes_host[i] are HOST pointers here; rows_per_block <= 0 picks ~96 MiB blocks.  Every buffer may be pinned
+ * (DMA straight from / to it) or pageable (staged block-wise through pinned scratch by XDEM_B200_HOST_THREADS host
+ * threads, default 4-8); the library detects which with cudaPointerGetAttributes. */
 int xb_terrain_fused_host(const void* dem_host, int dtype, int64_t rows, int64_t cols, double resolution, int fit_id,
                           int curv_method_id, uint32_t surf_mask, uint32_t win_mask, int window_size,
                           int tri_method_id, int degrees, int clip_hillshade, double hillshade_azimuth,
                           double hillshade_altitude, double hillshade_z_factor, void* const* out_planes_host,
                           int64_t rows_per_block);
+/* Row-range form: the host raster holds `rows` rows of which only [row_begin, row_end) are computed -- a row shard that
+ * carries `depth` halo rows of its neighbours (multi-GPU streaming of one raster, terrain.py:417-432); the planes have
+ * (row_end - row_begin) rows.  Rows outside [0, rows) count as NaN (raster border). */
+int xb_terrain_fused_host_rows(const void* dem_host, int dtype, int64_t rows, int64_t cols, int64_t row_begin,
+                               int64_t row_end, double resolution, int fit_id, int curv_method_id, uint32_t surf_mask,
+                               uint32_t win_mask, int window_size, int tri_method_id, int degrees, int clip_hillshade,
+                               double hillshade_azimuth, double hillshade_altitude, double hillshade_z_factor,
+                               void* const* out_planes_host, int64_t rows_per_block);
+/* Frees the device / pinned scratch the host-buffer path keeps between calls (3 slots of ~96 MiB x (1 + planes)). */
+int xb_release_scratch(void);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * N-D binned robust statistics -- the device side of `nd_binning` (xdem/spatialstats.py:91-216), i.e. of the

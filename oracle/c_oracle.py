@@ -71,6 +71,17 @@ def windowed_indexes(dem: np.ndarray, window_size: int, attrs: list[str], tri_me
     return out
 
 
+def rugosity(dem: np.ndarray, resolution: float, nthreads: int = 0) -> np.ndarray:
+    """Rugosity as the reference's Numba engine computes it (window.py:505-595), float32 DEM."""
+    dem = np.ascontiguousarray(dem, dtype=np.float32)
+    H, W = dem.shape
+    out = np.empty((H, W), dtype=np.float32)
+    rc = lib().xo_rugosity_f32(ctypes.c_void_p(dem.ctypes.data), ctypes.c_int64(H), ctypes.c_int64(W),
+                               ctypes.c_double(resolution), ctypes.c_void_p(out.ctypes.data), int(nthreads))
+    assert rc == 0
+    return out
+
+
 def variogram_pairs(coords: np.ndarray, values: np.ndarray, edges: np.ndarray, nthreads: int = 0
                     ) -> tuple[np.ndarray, np.ndarray, float]:
     """All-pairs lag binning (C/OpenMP): returns (count[int64], sumsq[float64], dmax)."""

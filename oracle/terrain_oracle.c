@@ -184,3 +184,60 @@ int xo_windowed_f32(const float* dem, int64_t H, int64_t W, int w, uint32_t attr
     }
     return 0;
 }
+
+/* rugosity (Jenness 2004), restating the per-pixel function the reference's Numba engine runs (window.py:505-595) with
+ * its type promotions: float32 segment arrays (dzs, dls, hsl = sqrt(dzs^2 + dls^2) / 2), the triangle half-perimeter
+ * `sum(T) / 2` and Heron product in float64, areas stored float32, `sum(A) / L**2` in float64.  Used for the CPU arm of
+ * the "all attributes" benchmark and checked against the Numba-engine fixtures (tests/test_oracle_terrain.py). */
+int xo_rugosity_f32(const float* dem, int64_t H, int64_t W, double resolution, float* out, int nthreads) {
+    static const int TRI[8][3] = {{3, 0, 12}, {0, 1, 8}, {1, 2, 9}, {2, 4, 14}, {4, 7, 15}, {7, 6, 11}, {6, 5, 10},
+                                  {5, 3, 13}};
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < H; ++r) {
+        for (int64_t c = 0; c < W; ++c) {
+            float Z[9];
+            int bad = 0;
+            for (int m1 = 0; m1 < 3; ++m1)
+                for (int m2 = 0; m2 < 3; ++m2) {
+                    const int64_t rr = r + m1 - 1, cc = c + m2 - 1;
+                    float v = NAN;
+                    if (rr >= 0 && rr < H && cc >= 0 && cc < W) v = dem[rr * W + cc];
+                    if (!isfinite(v)) bad = 1;
+                    Z[m1 * 3 + m2] = v;
+                }
+            if (bad) {
+                out[r * W + c] = NAN;
+                continue;
+            }
+            float dzs[16], dls[16], hsl[16];
+            int k = 0, all = 0;
+            for (int j = -1; j <= 1; ++j)
+                for (int i = -1; i <= 1; ++i) {
+                    if (j == 0 && i == 0) {
+                        ++all;
+                        continue;
+                    }
+                    dzs[k] = Z[4] - Z[all];
+                    dls[k] = (float)(sqrt((double)(j * j + i * i)) * resolution);
+                    ++all;
+                    ++k;
+                }
+            dzs[8] = Z[0] - Z[1], dzs[9] = Z[1] - Z[2], dzs[10] = Z[6] - Z[7], dzs[11] = Z[7] - Z[8];
+            dzs[12] = Z[0] - Z[3], dzs[13] = Z[3] - Z[6], dzs[14] = Z[2] - Z[5], dzs[15] = Z[5] - Z[8];
+            for (int i = 8; i < 16; ++i) dls[i] = (float)resolution;
+            for (int i = 0; i < 16; ++i) hsl[i] = sqrtf(dzs[i] * dzs[i] + dls[i] * dls[i]) / 2.0f;
+            float area = 0.0f;
+            for (int t = 0; t < 8; ++t) {
+                const float a = hsl[TRI[t][0]], b = hsl[TRI[t][1]], cc3 = hsl[TRI[t][2]];
+                const double hs = (double)((a + b) + cc3) / 2.0;
+                const float A = (float)sqrt(hs * (hs - a) * (hs - b) * (hs - cc3));
+                area += A;
+            }
+            out[r * W + c] = (float)((double)area / (resolution * resolution));
+        }
+    }
+    return 0;
+}

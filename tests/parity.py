@@ -44,6 +44,18 @@ def max_violation(x: np.ndarray, ref: np.ndarray, rtol: float, atol: float, peri
     return float(np.max(d / bound))
 
 
+def violation(x: np.ndarray, ref: np.ndarray, attr: str, degrees: bool = True, rtol: float = RTOL,
+              where: np.ndarray | None = None) -> float:
+    """Factor by which x violates the unwidened criterion against ref (<= 1 passes)."""
+    atol = ATOL.get(attr, 1e-6)
+    if attr in ("slope", "aspect") and not degrees:
+        atol *= np.pi / 180
+    period = (360.0 if degrees else 2 * np.pi) if attr == "aspect" else None
+    if where is not None:
+        x, ref = np.where(where, x, np.nan), np.where(where, ref, np.nan)
+    return max_violation(x, ref, rtol, atol, period)
+
+
 def assert_attr_close(x: np.ndarray, ref: np.ndarray, attr: str, degrees: bool = True, rtol: float = RTOL,
                       atol_scale: float = 1.0, where: np.ndarray | None = None, msg: str = "") -> None:
     assert x.shape == ref.shape, f"{msg}: shape {x.shape} vs {ref.shape}"

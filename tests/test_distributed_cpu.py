@@ -60,6 +60,49 @@ def _hist_worker(rank: int, world: int, port: int) -> None:
     dist.destroy_process_group()
 
 
+def _subgroup_worker(rank: int, world: int, port: int) -> None:
+    """World of 3 processes; the raster is sharded over the sub-group [1, 2] (group ranks 0, 1), which does not start at
+    global rank 0: halo peers must be translated to GLOBAL ranks (dist.P2POp addresses peers globally).  Also exercises
+    the overlapped schedule: interior rows first, neighbour strips after the halo rows arrived."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from xdem_b200.distributed import RowShard, _all_ranks_ok
+
+    sub = dist.new_group(ranks=[1, 2])
+    if rank in (1, 2):
+        gr, gw, rows, cols, depth = dist.get_rank(sub), 2, 7, 5, 2
+        full = torch.arange(gw * rows * cols, dtype=torch.float32).reshape(gw * rows, cols)
+        buf = torch.full((rows + 2 * depth, cols), float("nan"))
+        buf[depth:depth + rows] = full[gr * rows:(gr + 1) * rows]
+        shard = RowShard(gr, gw, depth, sub)
+        calls = []
+        out = torch.full((rows, cols), float("nan"))
+
+        def launch(view: torch.Tensor, rb: int, re: int, out_row0: int) -> None:
+            calls.append((rb, re, out_row0))
+            # a stand-in "stencil": every output row needs `depth` rows above and below unless at the raster border
+            for r in range(rb, re):
+                lo, hi = r - depth, r + depth
+                rows_needed = view[max(lo, 0):min(hi, view.shape[0] - 1) + 1]
+                assert not torch.isnan(rows_needed).any(), (gr, r)
+                out[out_row0 + (r - rb)] = view[r]
+
+        shard.run_overlapped(buf, rows, launch)
+        assert torch.equal(out, full[gr * rows:(gr + 1) * rows])
+        # interior first, then the strip next to the single neighbour
+        assert len(calls) == 2 and calls[0][1] - calls[0][0] == rows - depth and calls[1][1] - calls[1][0] == depth
+        # collective precondition check: one failing rank makes every rank see the failure
+        assert _all_ranks_ok(True, sub, torch.device("cpu")) is True
+        assert _all_ranks_ok(gr != 1, sub, torch.device("cpu")) is False
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_rowshard_subgroup_not_starting_at_rank0_gloo() -> None:
+    mp.spawn(_subgroup_worker, args=(3, _free_port()), nprocs=3, join=True)
+
+
 def test_histogram_allreduce_gloo() -> None:
     mp.spawn(_hist_worker, args=(2, _free_port()), nprocs=2, join=True)
 

@@ -61,7 +61,7 @@ def test_terrain_32768_properties(fit: str) -> None:
         keep = (to.get_terrain_attribute(crop, "slope", resolution=res, surface_fit=fit) > 1e-3)[h:-h, h:-h]
         for k, a in enumerate(attrs):
             # rows/cols cut by the crop are not raster borders in the full run
-            parity.assert_attr_close(got[k][h:-h, h:-h], ref[k][h:-h, h:-h], a, atol_scale=50.0, where=keep,
+            parity.assert_attr_close(got[k][h:-h, h:-h], ref[k][h:-h, h:-h], a, where=keep if a == "aspect" else None,
                                      msg=f"{fit} crop {r0},{c0}")
     # (4) row blocks with halo rows reproduce the single launch bit for bit (the multi-GPU / streaming contract)
     z -= 4096.0
@@ -86,6 +86,47 @@ def test_terrain_32768_properties(fit: str) -> None:
     assert float((inner[1] - aspect).abs().max()) <= 1e-5 * aspect + 1e-4
     if fit != "Horn":
         assert float(inner[2].abs().max()) <= 1e-6
+
+
+@pytest.mark.parametrize("fit", ["Florinsky", "ZevenbergThorne"])
+def test_benchmarked_dem_parity_on_crops(fit: str) -> None:
+    """The raster bench.py times (bench_data.device_fractal_dem, seed 42, 32768^2, |z| up to ~1e5 m) through the kernels
+    the benchmark launches, checked on crops against the float64 oracle at the UNWIDENED criterion
+    (|x - ref| <= 1e-5 |ref| + atol; reference accumulation: float64, surfit.py:1044): the four corners, the crop
+    holding the largest |z|, the crop holding the smallest |gradient| region sampled, and four interior crops --
+    for the headline 4-attribute request and for the 9-attribute request of BASELINE config 4."""
+    import torch
+
+    import bench_data
+    from oracle import terrain_oracle as to
+    from xdem_b200 import _engine
+
+    if _free_gb() < 60:
+        pytest.skip("needs ~45 GB of device memory")
+    S, res, h = 32768, 5.0, 2 if fit == "Florinsky" else 1
+    z = bench_data.device_fractal_dem(S, S, 42, torch.device("cuda"))
+    amax = int(torch.argmax(z.abs()))
+    r_hi, c_hi = min(max(amax // S - 32, 0), S - 64), min(max(amax % S - 48, 0), S - 96)
+    crops = [(0, 0), (0, S - 96), (S - 64, 0), (S - 64, S - 96), (r_hi, c_hi),
+             (4096, 4000), (12345, 23456), (20000, 9999), (30001, 16000), (16384 - 32, 16384 - 48)]
+    nine = ["slope", "aspect", "hillshade", "profile_curvature", "tangential_curvature", "planform_curvature",
+            "flowline_curvature", "max_curvature", "min_curvature"]
+    for attrs in (ATTRS, nine):
+        out = _engine.terrain_fused(z, res, attrs, [], surface_fit=fit, degrees=True, clip_hillshade=True)
+        worst = 0.0
+        for (r0, c0) in crops:
+            crop = z[r0:r0 + 64, c0:c0 + 96].cpu().numpy()
+            ref = to.get_terrain_attribute(crop, attrs, resolution=res, surface_fit=fit)
+            got = out[:, r0:r0 + 64, c0:c0 + 96].cpu().numpy()
+            keep = (to.get_terrain_attribute(crop.astype(np.float64), "slope", resolution=res, surface_fit=fit)
+                    > 1e-3)[h:-h, h:-h]
+            for k, a in enumerate(attrs):
+                g_, r_ = got[k][h:-h, h:-h], ref[k][h:-h, h:-h]
+                parity.assert_attr_close(g_, r_, a, where=keep if a == "aspect" else None,
+                                         msg=f"bench DEM {fit} crop {r0},{c0}")
+                worst = max(worst, parity.violation(g_, r_, a, where=keep if a == "aspect" else None))
+        print(f"bench DEM {fit} {len(attrs)} attrs: worst violation factor {worst:.3g} (<= 1 passes)")
+        del out
 
 
 def test_variogram_1e6_properties() -> None:

@@ -47,12 +47,19 @@ def test_surface_vs_reference_fixtures(xb, G, name: str, fit: str, cm: str) -> N
     outs = xb.terrain.get_terrain_attribute(dem, attrs, resolution=5.0, surface_fit=fit, curv_method=cm)
     keep = _keep(dem, fit)
     for a, o in zip(attrs, outs):
-        for engine in ("numba", "scipy"):
-            ref = G[f"surf|{name}|{engine}|{fit}|{cm}|deg|{a}"]
-            # the reference's SciPy engine rounds its coefficients to float32: its own two engines agree to ~1e-4 rel
-            # on near-zero values, so the SciPy fixtures get the wider absolute term
-            scale = (1.0 if engine == "numba" else 30.0) * (1.0 if name == "fractal" else 50.0)
-            parity.assert_attr_close(o, ref, a, where=keep, atol_scale=scale, msg=f"{name}/{engine}/{fit}/{cm}")
+        where = keep if a == "aspect" else None  # flat pixels are excluded for aspect only (test_terrain.py:168-169)
+        ref_n = G[f"surf|{name}|numba|{fit}|{cm}|deg|{a}"]
+        ref_s = G[f"surf|{name}|scipy|{fit}|{cm}|deg|{a}"]
+        # (1) the stated criterion, unwidened, against the reference's float64 (Numba) engine
+        parity.assert_attr_close(o, ref_n, a, where=where, msg=f"{name}/numba/{fit}/{cm}")
+        # (2) the SciPy engine rounds its coefficients to float32 (pinned bit-for-bit by the oracle's
+        # coef_round=float32 mode, tests/test_oracle_terrain.py).  Same criterion; where the reference's own two
+        # engines are further apart than that, the bound is their spread (triangle inequality), never a constant.
+        assert parity.nanmask_equal(o, ref_s), f"{name}/scipy/{fit}/{cm}: NaN masks differ"
+        v_gs = parity.violation(o, ref_s, a, where=where)
+        if v_gs > 1.0:
+            v_gn, v_ns = parity.violation(o, ref_n, a, where=where), parity.violation(ref_n, ref_s, a, where=where)
+            assert v_gs <= v_gn + v_ns * (1 + 1e-6), (name, fit, cm, a, v_gs, v_gn, v_ns)
 
 
 def test_radians_and_seam(xb, G) -> None:
@@ -66,7 +73,8 @@ def test_radians_and_seam(xb, G) -> None:
         assert seam.shape == (3,) + dem.shape and seam.dtype == np.float32
         for a, o in zip(["slope", "aspect"], out):
             ref = G[f"surf|fractal|numba|{fit}|geometric|rad|{a}"]
-            parity.assert_attr_close(o, ref, a, degrees=False, where=_keep(dem, fit), msg=f"rad {fit}")
+            parity.assert_attr_close(o, ref, a, degrees=False, where=_keep(dem, fit) if a == "aspect" else None,
+                                     msg=f"rad {fit}")
         assert np.array_equal(seam[2], out[0], equal_nan=True)
         assert np.array_equal(seam[0], out[1], equal_nan=True)
 
@@ -245,7 +253,7 @@ def test_odd_shapes_vs_oracle(xb, shape) -> None:
                 assert parity.nanmask_equal(o, r)
                 assert np.array_equal(o, r, equal_nan=True)
             else:
-                parity.assert_attr_close(o, r, a, where=keep, msg=f"{shape} {fit}")
+                parity.assert_attr_close(o, r, a, where=keep if a == "aspect" else None, msg=f"{shape} {fit}")
 
 
 def test_torch_cuda_tensor_in_out(xb) -> None:

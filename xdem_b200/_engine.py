@@ -58,10 +58,12 @@ def terrain_fused(
         row_end = rows_buf
     names = list(surface_attributes) + list(windowed_indexes)
     n_rows = row_end - row_begin
+    out_ld = cols
     if out is None:
         out = torch.empty((len(names), n_rows, cols), dtype=dem.dtype, device=dem.device)
-    elif out.shape != (len(names), n_rows, cols) or out.dtype != dem.dtype or not out.is_contiguous():
-        raise ValueError("bad `out` tensor")
+    elif out.shape != (len(names), n_rows, cols) or out.dtype != dem.dtype or (n_rows > 0 and out.stride(2) != 1):
+        raise ValueError("bad `out` tensor")  # planes may be row slices of a larger tensor (row stride = out_ld)
+    out_ld = out.stride(1) if n_rows > 1 else cols
     planes = (ctypes.c_void_p * N_PLANES)()
     surf_mask = 0
     win_mask = 0
@@ -84,7 +86,7 @@ def terrain_fused(
             dem.data_ptr(), _dtype_code(dem), rows_buf, cols, ld, row_begin, row_end, float(resolution),
             FIT_IDS[surface_fit.lower()], CURV_IDS[curv_method.lower()], surf_mask, win_mask, int(window_size),
             0 if tri_method.lower() == "riley" else 1, int(bool(degrees)), int(bool(clip_hillshade)),
-            float(hillshade_azimuth), float(hillshade_altitude), float(hillshade_z_factor), planes, cols,
+            float(hillshade_azimuth), float(hillshade_altitude), float(hillshade_z_factor), planes, int(out_ld),
             ctypes.c_void_p(stream))
     _lib.check(rc)
     return out
@@ -123,12 +125,19 @@ def terrain_fused_host(
     hillshade_azimuth: float = 315.0,
     hillshade_altitude: float = 45.0,
     hillshade_z_factor: float = 1.0,
-    out: np.ndarray | None = None,
+    out: "np.ndarray | Sequence[np.ndarray] | None" = None,
     rows_per_block: int = 0,
+    row_begin: int = 0,
+    row_end: int | None = None,
 ) -> np.ndarray:
-    """Host-buffer path (xb_terrain_fused_host): a C-contiguous float32/float64 NumPy raster is streamed through the GPU
-    in row blocks with halo rows (H2D / kernel / D2H overlapped); returns a (n_attr, H, W) NumPy array.  Pinned ``dem`` /
-    ``out`` buffers (e.g. views of torch pinned tensors) reach PCIe line rate; pageable ones work but copy slower."""
+    """Host-buffer path (xb_terrain_fused_host_rows): a C-contiguous float32/float64 NumPy raster is streamed through
+    the GPU in row blocks with halo rows (H2D / kernel / D2H overlapped); returns a (n_attr, rows, W) NumPy array.
+    ``dem`` may be pageable (a reference caller's ndarray: staged block-wise through pinned scratch by a few host
+    threads) or pinned.  When ``out`` is not given the planes are allocated in page-locked memory (torch's caching
+    host allocator recycles the blocks once the caller drops the array), so the device-to-host copies -- 4/5 of the
+    traffic of a 4-attribute request -- run at link rate; ``XDEM_B200_PINNED_OUTPUT=0`` allocates plain NumPy memory.
+    ``out`` may also be a (n_attr, rows, W) array or a list of (rows, W) planes to fill.
+    ``row_begin``/``row_end``: only these rows of ``dem`` are computed (the rest are halo rows of a row shard)."""
     if not torch.cuda.is_available():
         raise RuntimeError("xdem_b200 needs a CUDA device (B200, sm_100a): no CPU fallback exists.")
     if dem.ndim != 2 or dem.dtype not in (np.float32, np.float64):
@@ -136,24 +145,43 @@ def terrain_fused_host(
     dem = np.ascontiguousarray(dem)
     L = _lib.lib()
     rows, cols = dem.shape
+    if row_end is None:
+        row_end = rows
+    n_rows = row_end - row_begin
     names = list(surface_attributes) + list(windowed_indexes)
     if out is None:
-        out = np.empty((len(names), rows, cols), dtype=dem.dtype)
-    elif out.shape != (len(names), rows, cols) or out.dtype != dem.dtype or not out.flags.c_contiguous:
-        raise ValueError("bad `out` array")
+        out = host_planes(len(names), n_rows, cols, dem.dtype)
+    if len(out) != len(names) or any(o.shape != (n_rows, cols) or o.dtype != dem.dtype or not o.flags.c_contiguous
+                                     for o in out):
+        raise ValueError("bad `out`: one C-contiguous (rows, cols) plane of the raster's dtype per attribute")
     surf_mask, win_mask, slots = _masks_and_slots(surface_attributes, windowed_indexes)
     planes = (ctypes.c_void_p * N_PLANES)()
     for i, slot in enumerate(slots):
         planes[slot] = out[i].ctypes.data
     with torch.cuda.device(torch.cuda.current_device()):
-        rc = L.xb_terrain_fused_host(
-            ctypes.c_void_p(dem.ctypes.data), 0 if dem.dtype == np.float32 else 1, rows, cols, float(resolution),
-            FIT_IDS[surface_fit.lower()], CURV_IDS[curv_method.lower()], surf_mask, win_mask, int(window_size),
-            0 if tri_method.lower() == "riley" else 1, int(bool(degrees)), int(bool(clip_hillshade)),
-            float(hillshade_azimuth), float(hillshade_altitude), float(hillshade_z_factor), planes,
-            int(rows_per_block))
+        rc = L.xb_terrain_fused_host_rows(
+            ctypes.c_void_p(dem.ctypes.data), 0 if dem.dtype == np.float32 else 1, rows, cols, int(row_begin),
+            int(row_end), float(resolution), FIT_IDS[surface_fit.lower()], CURV_IDS[curv_method.lower()], surf_mask,
+            win_mask, int(window_size), 0 if tri_method.lower() == "riley" else 1, int(bool(degrees)),
+            int(bool(clip_hillshade)), float(hillshade_azimuth), float(hillshade_altitude), float(hillshade_z_factor),
+            planes, int(rows_per_block))
     _lib.check(rc)
     return out
+
+
+def host_planes(n: int, rows: int, cols: int, dtype: np.dtype) -> np.ndarray:
+    """(n, rows, cols) output planes for the host-buffer path: a NumPy view of page-locked memory from torch's caching
+    host allocator (kept alive by the array's base), or plain NumPy memory when XDEM_B200_PINNED_OUTPUT=0 or the
+    pinned allocation fails."""
+    import os
+
+    if os.environ.get("XDEM_B200_PINNED_OUTPUT", "1") != "0" and n * rows * cols > 0:
+        try:
+            t = torch.empty((n, rows, cols), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+            return t.numpy()
+        except RuntimeError:
+            pass
+    return np.empty((n, rows, cols), dtype=dtype)
 
 
 GENERIC_SLOTS = {"topographic_position_index": 0, "terrain_ruggedness_index": 1, "roughness": 2, "fractal_roughness": 4}

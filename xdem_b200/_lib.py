@@ -40,6 +40,11 @@ def lib() -> ctypes.CDLL:
         L.xb_terrain_fused_host.argtypes = [c_void_p, c_int, c_int64, c_int64, c_double, c_int, c_int, c_uint32,
                                             c_uint32, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
                                             ctypes.POINTER(c_void_p), c_int64]
+    L.xb_terrain_fused_host_rows.restype = c_int
+    L.xb_terrain_fused_host_rows.argtypes = [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_double, c_int, c_int,
+                                             c_uint32, c_uint32, c_int, c_int, c_int, c_int, c_double, c_double,
+                                             c_double, ctypes.POINTER(c_void_p), c_int64]
+    L.xb_release_scratch.restype = c_int
     L.xb_set_option.restype = c_int
     L.xb_set_option.argtypes = [c_char_p, c_int]
     L.xb_windowed_generic.restype = c_int
@@ -120,6 +125,7 @@ EXPORTED = ["xb_last_error", "xb_version", "xb_launch_count", "xb_terrain_fused"
             "xb_variogram_group_size", "xb_variogram_chunk", "xb_variogram_pairs", "xb_variogram_median_pass", "xb_variogram_maxd2", "xb_nk_aux",
             "xb_nk_dh", "xb_nk_hist", "xb_nk_next", "xb_nk_make_keys", "xb_nk_hist_keys", "xb_nk_next_keys",
             "xb_windowed_generic", "xb_set_option", "xb_shift_resample", "xb_texture_prepare", "xb_texture_filter",
-            "xb_texture_finish", "xb_bin_keys", "xb_bin_hist", "xb_bin_next", "xb_bin_absdev_keys", "xb_probe_stream", "xb_probe_exact_math"]
+            "xb_texture_finish", "xb_bin_keys", "xb_bin_hist", "xb_bin_next", "xb_bin_absdev_keys", "xb_probe_stream", "xb_probe_exact_math",
+            "xb_terrain_fused_host_rows", "xb_release_scratch"]
 
 __all__ = ["lib", "check", "launch_count", "set_option", "XdemB200Error", "LIB_PATH", "EXPORTED"]

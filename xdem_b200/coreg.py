@@ -340,6 +340,30 @@ def nuth_kaab(ref_elev: Any, tba_elev: Any, inlier_mask: Any = None, transform: 
     return offsets, n_valid
 
 
+def make_reference_hook(reference_nuth_kaab: Callable[..., Any]) -> Callable[..., Any]:
+    """Wrapper with the signature of ``xdem.coreg.affine.nuth_kaab`` (affine.py:539-553) for ``xdem_b200.install()``:
+    raster-raster fits with the reference defaults (bin_and_fit, integer bin count, np.nanmedian) run on the GPU,
+    everything else (point clouds, ``fit_or_bin="fit"``, custom statistics, weights) is handed to the reference
+    function it replaces -- so the rebinding never narrows what ``NuthKaab.fit`` accepts."""
+
+    def nuth_kaab_hook(ref_elev: Any, tba_elev: Any, inlier_mask: Any, transform: Any, crs: Any, area_or_point: Any,
+                       tolerance: float, max_iterations: int, params_fit_or_bin: dict[str, Any],
+                       params_random: dict[str, Any], z_name: str, weights: Any = None, **kwargs: Any) -> Any:
+        pf = params_fit_or_bin or {}
+        on_path = (isinstance(ref_elev, (np.ndarray, torch.Tensor)) and isinstance(tba_elev, (np.ndarray, torch.Tensor))
+                   and weights is None and pf.get("fit_or_bin", "bin_and_fit") == "bin_and_fit"
+                   and pf.get("bin_statistic", np.nanmedian) is np.nanmedian
+                   and isinstance(pf.get("bin_sizes", 72), (int, np.integer)))
+        fn = nuth_kaab if on_path else reference_nuth_kaab
+        return fn(ref_elev=ref_elev, tba_elev=tba_elev, inlier_mask=inlier_mask, transform=transform, crs=crs,
+                  area_or_point=area_or_point, tolerance=tolerance, max_iterations=max_iterations,
+                  params_fit_or_bin=params_fit_or_bin, params_random=params_random, z_name=z_name, weights=weights,
+                  **kwargs)
+
+    nuth_kaab_hook.__wrapped__ = reference_nuth_kaab  # type: ignore[attr-defined]
+    return nuth_kaab_hook
+
+
 def _iterate_nuth_kaab(state: _NKState, transform: Any, bin_sizes: int, fit_optimizer: Callable[..., Any],
                        tolerance: float, max_iterations: int) -> tuple[float, float, float]:
     """`_iterate_method` (affine.py:102-147) around the GPU iteration step."""

@@ -172,6 +172,9 @@ int xb_build_terrain_params(xbt::TerrainParams& p, int dtype, double resolution,
     p.f.rug_nll = -(float)p.rug_ll;
     p.f.rug_l2s = (float)p.rug_dl2_straight;
     p.f.rug_l2d = (float)p.rug_dl2_diag;
+    p.f.one = 1.0f;
+    p.f.rug_y4 = -0.25f * p.f.rug_rcp_ll;
+    p.f.rug_b4 = -4.0f * p.f.rug_nll;
     *hs_out = hs;
     *hw_out = hw;
     return XB_OK;
@@ -250,9 +253,7 @@ int xb_terrain_fused(const void* dem_dev, int dtype, int64_t rows_buf, int64_t c
     p.row_end = row_end;
     p.out_ld = out_ld;
     if (row_end == row_begin) return XB_OK;
-    rc = xbt::launch(p, dtype, hs, hw, reinterpret_cast<cudaStream_t>(stream));
-    if (rc == XB_OK) g_launches.fetch_add(1);
-    return rc;
+    return xbt::launch(p, dtype, hs, hw, reinterpret_cast<cudaStream_t>(stream));  // counts its kernel launches itself
 }
 
 #pragma GCC visibility pop

@@ -12,6 +12,7 @@
 #define XB_ERR_UNSUPPORTED (-3)
 
 void xb_set_error(const char* fmt, ...);
+void xb_count_launch(int n);  // every kernel launch of the library is counted (xb_launch_count)
 
 #define XB_CUDA_CHECK(expr)                                                                       \
     do {                                                                                          \

@@ -111,8 +111,11 @@ __device__ __forceinline__ Derivs<T> derivs_at(const T (&win)[2 * H + 1][4 + 2 *
             v2[c + 2] = WIN(-2, c) - WIN(2, c);
             v1[c + 2] = WIN(1, c) - WIN(-1, c);
         }
-        d.sy = T(31) * (v2[0] + v2[4]) - T(5) * (v2[1] + v2[3]) - T(17) * v2[2] + T(44) * (v1[0] + v1[4]) +
-               T(62) * (v1[1] + v1[3]) + T(68) * v1[2];
+        // the weights sum to 35 (v2) and 280 (v1) and the two parts cancel on steep, curved surfaces: combine them at the
+        // level of the differences first -- 35 (v2c + 8 v1c) + sum_c a_c (v2_c - v2c) + b_c (v1_c - v1c)
+        d.sy = T(35) * (v2[2] + T(8) * v1[2]) + T(31) * ((v2[0] + v2[4]) - T(2) * v2[2]) -
+               T(5) * ((v2[1] + v2[3]) - T(2) * v2[2]) + T(44) * ((v1[0] + v1[4]) - T(2) * v1[2]) +
+               T(62) * ((v1[1] + v1[3]) - T(2) * v1[2]);
         // z_x: sum_r a_r (W(r,2) - W(r,-2)) + b_r (W(r,-1) - W(r,1))
         T dd[5], ee[5];
 #pragma unroll
@@ -120,8 +123,9 @@ __device__ __forceinline__ Derivs<T> derivs_at(const T (&win)[2 * H + 1][4 + 2 *
             dd[r + 2] = WIN(r, 2) - WIN(r, -2);
             ee[r + 2] = WIN(r, -1) - WIN(r, 1);
         }
-        d.sx = T(31) * (dd[0] + dd[4]) - T(5) * (dd[1] + dd[3]) - T(17) * dd[2] + T(44) * (ee[0] + ee[4]) +
-               T(62) * (ee[1] + ee[3]) + T(68) * ee[2];
+        d.sx = T(35) * (dd[2] + T(8) * ee[2]) + T(31) * ((dd[0] + dd[4]) - T(2) * dd[2]) -
+               T(5) * ((dd[1] + dd[3]) - T(2) * dd[2]) + T(44) * ((ee[0] + ee[4]) - T(2) * ee[2]) +
+               T(62) * ((ee[1] + ee[3]) - T(2) * ee[2]);
         d.carrier = (d.sx + d.sy + WIN(0, 0)) * T(0);
         if (need2) {
             // z_xx: every row [2,-1,-2,-1,2]  -> second differences first (exact), then the 5-row sum
@@ -497,6 +501,7 @@ static int launch_cfg(const CUtensorMap& tmap, const TerrainParams& p, int num_s
     if (grid > p.ntiles) grid = p.ntiles;
     kern<<<(unsigned)grid, NTHREADS, smem, stream>>>(tmap, p);
     XB_CUDA_CHECK(cudaGetLastError());
+    xb_count_launch(1);
     return XB_OK;
 }
 

@@ -69,13 +69,20 @@ __device__ __forceinline__ void emit_row(const RowFeat& r0, const RowFeat& r1, c
     float sx[2], sy[2], sxx[2], syy[2], sxy[2], car[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-        // z_x (fl_p, divider 420 res)
-        sx[k] = 31.0f * (r0.D[k] + r4.D[k]) - 5.0f * (r1.D[k] + r3.D[k]) - 17.0f * r2.D[k] +
-                44.0f * (r0.E[k] + r4.E[k]) + 62.0f * (r1.E[k] + r3.E[k]) + 68.0f * r2.E[k];
-        // z_y (fl_q): row sums about the row centres + the centre-column differences
+        // z_x (fl_p, divider 420 res): the column weights sum to 35 (D) and 280 (E) and on a surface that is steep but
+        // curved across x the two parts cancel; they are combined at the level of the differences FIRST --
+        // 35 (D2 + 8 E2) + sum_r a_r (D_r - D2) + b_r (E_r - E2) -- so that the large parts cancel exactly and only
+        // small second-order terms meet the big weights (see DESIGN.md "Numerical design")
+        {
+            const float s1 = fmaf(-2.0f, r2.D[k], r0.D[k] + r4.D[k]), s2 = fmaf(-2.0f, r2.D[k], r1.D[k] + r3.D[k]);
+            const float s3 = fmaf(-2.0f, r2.E[k], r0.E[k] + r4.E[k]), s4 = fmaf(-2.0f, r2.E[k], r1.E[k] + r3.E[k]);
+            const float tx = fmaf(8.0f, r2.E[k], r2.D[k]);
+            sx[k] = fmaf(35.0f, tx, fmaf(31.0f, s1, fmaf(-5.0f, s2, fmaf(44.0f, s3, 62.0f * s4))));
+        }
+        // z_y (fl_q): row sums about the row centres + the centre-column differences (same ordering rule)
         sy[k] = (31.0f * (r0.p[k] - r4.p[k]) - 5.0f * (r0.q[k] - r4.q[k])) +
                 (44.0f * (r3.p[k] - r1.p[k]) + 62.0f * (r3.q[k] - r1.q[k])) +
-                (35.0f * (r0.c[k] - r4.c[k]) + 280.0f * (r3.c[k] - r1.c[k]));
+                35.0f * fmaf(8.0f, r3.c[k] - r1.c[k], r0.c[k] - r4.c[k]);
         const float pp2 = r0.p[k] + r4.p[k], pp1 = r1.p[k] + r3.p[k];
         const float qq2 = r0.q[k] + r4.q[k], qq1 = r1.q[k] + r3.q[k];
         // z_xx (fl_r, 35 res^2) = sum_r (2 p_r - q_r): propagates NaN / inf from every cell of the 5x5 window
@@ -190,17 +197,20 @@ __device__ __forceinline__ void emit_row(const RowFeat2& r0, const RowFeat2& r1,
     static_assert(CMASK != 0, "packed path: compile-time attribute mask");
     constexpr bool NEED2 = (CMASK & ~7u) != 0;    // any second-derivative attribute
     constexpr bool NEEDALG = (CMASK & ~15u) != 0;  // curvature algebra (per-pixel FP64 numerators, curv_alg<float>)
-    // z_x (fl_p, divider 420 res)
-    f2 sx = mul2(S2(31.0f), add2(r0.D, r4.D));
-    sx = fma2(S2(-5.0f), add2(r1.D, r3.D), sx);
-    sx = fma2(S2(-17.0f), r2.D, sx);
-    sx = fma2(S2(44.0f), add2(r0.E, r4.E), sx);
-    sx = fma2(S2(62.0f), add2(r1.E, r3.E), sx);
-    sx = fma2(S2(68.0f), r2.E, sx);
+    // z_x (fl_p, divider 420 res): 35 (D2 + 8 E2) + sum_r a_r (D_r - D2) + b_r (E_r - E2) -- the large, mutually
+    // cancelling D and E parts are combined exactly at the level of the differences before any big weight is applied
+    const f2 s1 = fma2(S2(-2.0f), r2.D, add2(r0.D, r4.D)), s2 = fma2(S2(-2.0f), r2.D, add2(r1.D, r3.D));
+    const f2 s3 = fma2(S2(-2.0f), r2.E, add2(r0.E, r4.E)), s4 = fma2(S2(-2.0f), r2.E, add2(r1.E, r3.E));
+    const f2 tx = fma2(S2(8.0f), r2.E, r2.D);
+    f2 sx = mul2(S2(62.0f), s4);
+    sx = fma2(S2(44.0f), s3, sx);
+    sx = fma2(S2(-5.0f), s2, sx);
+    sx = fma2(S2(31.0f), s1, sx);
+    sx = fma2(S2(35.0f), tx, sx);
     // z_y (fl_q)
     const f2 t1 = fma2(S2(-5.0f), sub2(r0.q, r4.q), mul2(S2(31.0f), sub2(r0.p, r4.p)));
     const f2 t2 = fma2(S2(62.0f), sub2(r3.q, r1.q), mul2(S2(44.0f), sub2(r3.p, r1.p)));
-    const f2 t3 = fma2(S2(280.0f), sub2(r3.c, r1.c), mul2(S2(35.0f), sub2(r0.c, r4.c)));
+    const f2 t3 = mul2(S2(35.0f), fma2(S2(8.0f), sub2(r3.c, r1.c), sub2(r0.c, r4.c)));
     const f2 sy = add2(add2(t1, t2), t3);
     f2 pp2, pp1, qq2, qq1, nsxx, car;
     if constexpr (NEED2) {
@@ -435,6 +445,7 @@ int launch_florinsky_sliding(const TerrainParams& p_in, cudaStream_t stream) {
         if (grid > p.ntiles) grid = p.ntiles;
         kern<<<(unsigned)grid, NTHREADS, smem, stream>>>(tmap, p);
         XB_CUDA_CHECK(cudaGetLastError());
+        xb_count_launch(1);
         return XB_OK;
     };
     // 2 CTAs/SM: the 5-row feature ring needs ~100 registers (a 3-CTA build spills and measured 40 % slower).
