@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from fractions import Fraction
 from typing import Any, Iterable
 
@@ -34,9 +35,25 @@ def _float_distance(d2: int, gsd: float) -> float:
     return math.sqrt(gsd * gsd * d2)
 
 
-def edge_thresholds(edges: Iterable[float], gsd: float) -> list[int]:
-    """Integer thresholds T_k on the squared pixel distance with  d < edge_k  <=>  d2 < T_k  under the reference's
-    float64 comparison: T_k = smallest integer d2 whose float64 distance is >= edge_k."""
+#: Which side of a lag class is closed.  "left" = edges[k-1] <= d < edges[k], the rule restated from scikit-gstat 1.0.x
+#: (``Variogram._calc_groups``); "right" = edges[k-1] < d <= edges[k].  scikit-gstat is absent from the reference tree and
+#: from this image, so the rule is UNPINNED: the two only differ for pairs that sit exactly on a bin
+#: edge, both are implemented (the rule only changes the integer thresholds built on the host) and pinned by hand-checkable
+#: golden cases (tests/golden/variogram_edges.json), and this one flag -- or XDEM_B200_LAG_EDGE_RULE -- selects it.
+LAG_EDGE_RULE = os.environ.get("XDEM_B200_LAG_EDGE_RULE", "left")
+
+
+def edge_thresholds(edges: Iterable[float], gsd: float, rule: str | None = None) -> list[int]:
+    """Integer thresholds T_k on the squared pixel distance such that a pair belongs to lag class k  <=>
+    T_{k-1} <= d2 < T_k, reproducing the reference's float64 comparison of d = sqrt(gsd^2 d2) with the edges:
+    rule "left":  d < edge_k  <=>  d2 < T_k,  T_k = smallest integer d2 whose float64 distance is >= edge_k;
+    rule "right": d <= edge_k <=>  d2 < T_k,  T_k = smallest integer d2 whose float64 distance is >  edge_k.
+    Exact whenever index*gsd and its squares are exact in float64 (integer or dyadic gsd); for other gsd the
+    reference's per-pair rounding of the coordinates can move pairs that sit on an edge to the neighbouring class
+    (see ``on_edge_pair_bound``)."""
+    rule = rule or LAG_EDGE_RULE
+    if rule not in ("left", "right"):
+        raise ValueError(f"lag edge rule must be 'left' or 'right', got {rule!r}")
     out = []
     for e in edges:
         e = float(e)
@@ -44,12 +61,34 @@ def edge_thresholds(edges: Iterable[float], gsd: float) -> list[int]:
             out.append(0)
             continue
         c = int(math.ceil(Fraction(e) ** 2 / Fraction(gsd) ** 2))
-        while c > 0 and _float_distance(c - 1, gsd) >= e:
-            c -= 1
-        while _float_distance(c, gsd) < e:
-            c += 1
+        if rule == "left":
+            while c > 0 and _float_distance(c - 1, gsd) >= e:
+                c -= 1
+            while _float_distance(c, gsd) < e:
+                c += 1
+        else:
+            while c > 0 and _float_distance(c - 1, gsd) > e:
+                c -= 1
+            while _float_distance(c, gsd) <= e:
+                c += 1
         out.append(min(c, (1 << 63) - 1))
     return out
+
+
+def on_edge_d2(edges: Iterable[float], gsd: float, ulps: int = 4) -> list[int]:
+    """Integer squared pixel distances whose float64 distance lies within ``ulps`` ulp of a bin edge: the only pairs
+    whose class can depend on how the reference rounds the individual coordinates (non-dyadic gsd) -- with the default
+    sqrt(2)-geometric edges these are the lattice distances d2 = 2^k."""
+    out = []
+    for e in edges:
+        e = float(e)
+        if not e > 0:
+            continue
+        c0 = int(round((e / gsd) ** 2))
+        for c in range(max(c0 - 1, 0), c0 + 2):
+            if abs(_float_distance(c, gsd) - e) <= ulps * math.ulp(e):
+                out.append(c)
+    return sorted(set(out))
 
 
 def _spread_bits16(v: torch.Tensor) -> torch.Tensor:
@@ -98,7 +137,7 @@ def _unit_prefix(n_groups: int) -> np.ndarray:
 
 def pairwise_lag_binning(x: torch.Tensor, y: torch.Tensor, v: torch.Tensor, edges: np.ndarray | None, gsd: float,
                          n_lags: int | None = None, maxlag: float | None = None, group: Any = None,
-                         estimator: str = "matheron", distributed: bool = False
+                         estimator: str = "matheron", distributed: bool = False, edge_rule: str | None = None
                          ) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
     """All-pairs lag binning of N grid samples (integer pixel coordinates x, y; float32 values v) on the GPU.
 
@@ -133,7 +172,7 @@ def pairwise_lag_binning(x: torch.Tensor, y: torch.Tensor, v: torch.Tensor, edge
             top = dmax if (maxlag is None or maxlag > dmax) else maxlag
             edges = np.linspace(0, top, int(n_lags) + 1)[1:]
         edges = np.asarray(edges, dtype=np.float64)
-        e2 = torch.tensor(edge_thresholds(edges, gsd), dtype=torch.int64, device=dev)
+        e2 = torch.tensor(edge_thresholds(edges, gsd, edge_rule), dtype=torch.int64, device=dev)
         if not bool((e2[1:] >= e2[:-1]).all()):
             raise ValueError("bin edges must be ascending")
         prefix_np = _unit_prefix(n_groups)
