@@ -211,6 +211,26 @@ int xb_variogram_median_pass(const int32_t* pts_dev, const int32_t* gbox_dev, in
 int xb_variogram_maxd2(const int32_t* pts_dev, const int32_t* gbox_dev, int64_t n_groups,
                        unsigned long long* maxd2_dev, void* stream);
 
+/* General-coordinate form of the pair binning (float64 coordinates and values): every pair i < j of one sample set
+ * (xb_dev == NULL; `_get_pdist_empirical_variogram`, spatialstats.py:1064-1101, incl. 1-D values + `coords=`) or every
+ * pair between two sets A x B (`_get_cdist_empirical_variogram`, spatialstats.py:1186-1261: centre-disk x ring samples
+ * of the default `cdist_equidistant` sampler, the two random subsets of `cdist_point`).  Squared distance exactly as
+ * scipy / cKDTree form it in float64, d2 = RN(RN(dx dx) + RN(dy dy)); thr_d2_dev[k] = the float64 threshold on d2 the
+ * host derives from right edge k (d < edge <=> d2 < thr, sqrt being monotone); class = first k with d2 < thr[k], pairs
+ * with d2 >= thr[n_bins-1] are dropped.  estimator 0: sum_dev[k] += (v_i - v_j)^2; 1: += |v_i - v_j|^0.5;
+ * 2 (Dowd): nothing is summed, pair_class_dev[i*nb + j] (0xFFFF = no class) and pair_key_dev[i*nb + j] (order-preserving
+ * key of float32 |v_i - v_j|, as xb_bin_keys builds it) are written for the radix select of xb_bin_hist / xb_bin_next.  maxd2_bits_dev (optional): bit pattern
+ * of the largest d2 over all pairs (atomicMax; skgstat's "even" binning clips maxlag to the largest distance).
+ * ida/idb (optional, A x B only): sample identities; a pair of a sample with itself is skipped, and a pair whose two
+ * samples both carry dupa/dupb != 0 (they belong to BOTH sets, so the pair occurs in both orientations) is only taken in
+ * the orientation ida < idb. */
+int xb_variogram_pairs_xy(const double* xa_dev, const double* ya_dev, const double* va_dev, int64_t na,
+                          const double* xb_dev, const double* yb_dev, const double* vb_dev, int64_t nb,
+                          const double* thr_d2_dev, int n_bins, int estimator, unsigned long long* count_dev,
+                          double* sum_dev, unsigned long long* maxd2_bits_dev, uint16_t* pair_class_dev,
+                          uint32_t* pair_key_dev, const int64_t* ida_dev, const int64_t* idb_dev,
+                          const uint8_t* dupa_dev, const uint8_t* dupb_dev, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Nuth & Kaab (2011) inner step.
  * xb_nk_aux replaces `_nuth_kaab_aux_vars` + the zero-slope mask (affine.py:412-474, 578-579): np.gradient semantics

@@ -140,8 +140,17 @@ def test_variogram_and_coreg_validation_without_gpu() -> None:
         xs.sample_empirical_variogram(v2.ravel(), gsd=1.0, subsample=10, subsample_method="pdist_point")
     with pytest.raises(TypeError, match="subsampling method must be one of"):
         xs.sample_empirical_variogram(v2, gsd=1.0, subsample_method="nope")
-    with pytest.raises(NotImplementedError):
-        xs.sample_empirical_variogram(v2, gsd=1.0)  # default scikit-gstat equidistant sampler
+    with pytest.raises(NotImplementedError, match="estimator"):
+        xs.sample_empirical_variogram(v2, gsd=1.0, estimator="genton")
+    with pytest.raises(RuntimeError, match="CUDA device"):  # the default (equidistant) sampler is on the path: no fallback
+        xs.sample_empirical_variogram(v2, gsd=1.0)
+    with pytest.raises(ValueError, match="at least"):
+        xs._choose_cdist_equidistant_sampling_parameters(extent=(0, 7, 0, 7), shape=(8, 8), subsample=5)
+    # the reference's own parameter split (spatialstats.py:1104-1183): subsample 1000 -> 100 runs x 23 samples... checked
+    # against the unmodified reference function in tests/test_reference_hooks.py when /root/reference is present
+    runs, samples, ratio = xs._choose_cdist_equidistant_sampling_parameters(extent=(0, 99, 0, 99), shape=(100, 100),
+                                                                            subsample=1000)
+    assert runs * samples**2 * 10 >= 1000**2 / 2 and 0 < ratio < 1
     with pytest.raises(TypeError, match="`fit_optimizer` must be a function"):
         coreg.NuthKaab(fit_optimizer=3)  # type: ignore
     with pytest.raises(TypeError, match="`bin_sizes` must be an integer"):

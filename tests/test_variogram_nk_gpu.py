@@ -71,10 +71,134 @@ def test_sample_empirical_variogram_frame() -> None:
     df3 = xs.sample_empirical_variogram(vals, gsd=5.0, subsample=400, subsample_method="pdist_point", n_variograms=3,
                                         random_state=7, bin_func="even", n_lags=20)
     assert len(df3) >= 19 and (df3["count"] > 0).any()
-    with pytest.raises(NotImplementedError):
-        xs.sample_empirical_variogram(vals, gsd=5.0, subsample=100)  # default cdist_equidistant sampler
+    # the reference's DEFAULT call (cdist_equidistant sampler, spatialstats.py:1301) is on the path
+    dfd = xs.sample_empirical_variogram(vals, gsd=5.0, subsample=100, random_state=11)
+    assert list(dfd.columns) == ["exp", "lags", "count", "err_exp"] and len(dfd) == len(edges) - 1
+    assert dfd["count"].sum() > 0 and np.isfinite(dfd["exp"][dfd["count"] > 0]).all()
     with pytest.raises(ValueError, match="ground sampling distance must be defined"):
         xs.sample_empirical_variogram(vals, subsample=100, subsample_method="pdist_point")
+
+
+def _edge_golden() -> dict:
+    import json
+    import os
+
+    with open(os.path.join(parity.GOLDEN, "variogram_edges.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("rule", ["left", "right"])
+@pytest.mark.parametrize("gsd", [1.0, 5.0, 0.5])
+def test_pair_kernels_on_edge_goldens_both_rules(rule: str, gsd: float) -> None:
+    """Pairs sitting EXACTLY on bin edges -- the only pairs on which the two possible conventions of scikit-gstat's lag
+    classes differ (PARITY UNPINNED) -- against the hand-checkable exact-integer golden cases, for BOTH conventions and
+    BOTH kernels (integer grid kernel, float64-coordinate kernel).  The product's rule is one flag
+    (xdem_b200.spatialstats.LAG_EDGE_RULE); whichever skgstat turns out to use, the matching counts are pinned here."""
+    from fractions import Fraction
+
+    import torch
+
+    from xdem_b200 import spatialstats as xs
+
+    for c in _edge_golden()["cases"]:
+        e_sq = [Fraction(n, d) for n, d in c["edges_sq_num_den"]]
+        if not all(float(np.sqrt(float(q))) ** 2 == float(q) for q in e_sq):
+            continue  # irrational edges: the float edge is a rounded neighbour of the lattice distance (CPU test)
+        edges = np.array([gsd * float(np.sqrt(float(q))) for q in e_sq])
+        pts = np.asarray(c["points"], dtype=np.int64)
+        vals = np.asarray(c["values"], dtype=np.float32)
+        x, y, v = (torch.from_numpy(a).cuda() for a in (pts[:, 0].copy(), pts[:, 1].copy(), vals))
+        want_cnt = np.asarray(c[rule]["count"])
+        want_ssq = np.asarray([n / d for n, d in c[rule]["sumsq"]])
+        _, cnt, ssq = xs.pairwise_lag_binning(x, y, v, edges, gsd, edge_rule=rule)
+        assert np.array_equal(cnt, want_cnt) and np.allclose(ssq, want_ssq, rtol=1e-12), (c["name"], rule, "grid")
+        ps = xs.PairSet(pts[:, 0] * gsd, pts[:, 1] * gsd, vals.astype(np.float64))
+        _, cnt2, ssq2 = xs.pairwise_lag_binning_xy(ps, edges, edge_rule=rule)
+        assert np.array_equal(cnt2, want_cnt) and np.allclose(ssq2, want_ssq, rtol=1e-12), (c["name"], rule, "xy")
+
+
+@pytest.mark.parametrize("estimator", ["matheron", "cressie", "dowd"])
+@pytest.mark.parametrize("gsd", [5.0, 0.1, 0.7])
+def test_xy_kernel_vs_float64_oracle(estimator: str, gsd: float) -> None:
+    """float64-coordinate kernel == the pdist-based oracle: counts identical for ANY spacing (incl. non-dyadic gsd,
+    where the integer kernel is only exact off the edges), estimators within float64 / float32-key round-off; both
+    through `_get_pdist_empirical_variogram` (the function install() rebinds) and with arbitrary scattered points."""
+    from oracle import variogram_oracle as vo
+    from xdem_b200 import spatialstats as xs
+
+    rng = np.random.default_rng(21)
+    shape = (70, 90)
+    coords = vo.grid_coords(shape, gsd)
+    vals = rng.normal(size=shape[0] * shape[1]).astype(np.float32)
+    idx = rng.choice(vals.size, 900, replace=False)
+    maxlag = float(np.hypot(coords[:, 0].max(), coords[:, 1].max()))
+    for bins in (vo.default_bins(gsd, maxlag), "even"):
+        b_o, exp_o, cnt_o = vo.empirical_variogram(coords[idx], vals[idx], bins, n_lags=17, maxlag=maxlag,
+                                                   estimator=estimator)
+        df = xs._get_pdist_empirical_variogram(values=vals[idx], coords=coords[idx], bin_func=bins, n_lags=17,
+                                               maxlag=maxlag, estimator=estimator, random_state=None)
+        assert np.array_equal(df["bins"].values, b_o)
+        assert np.array_equal(df["count"].values, cnt_o)
+        assert np.allclose(df["exp"].values, exp_o, rtol=2e-6 if estimator == "dowd" else 1e-12, equal_nan=True)
+    # scattered float coordinates, two sets (cdist): brute force in NumPy
+    a, b = rng.uniform(0, 100, (300, 2)), rng.uniform(0, 100, (450, 2))
+    va, vb = rng.normal(size=300), rng.normal(size=450)
+    edges = np.linspace(0, 150, 13)[1:]
+    d = np.sqrt((a[:, None, 0] - b[None, :, 0]) ** 2 + (a[:, None, 1] - b[None, :, 1]) ** 2)
+    df2 = np.abs(va[:, None] - vb[None, :])
+    lo = np.concatenate([[0.0], edges[:-1]])
+    cnt_w = np.array([int(((d >= lo[k]) & (d < edges[k])).sum()) for k in range(len(edges))])
+    _, cnt, third = xs.pairwise_lag_binning_xy(xs.PairSet(a[:, 0], a[:, 1], va, b[:, 0], b[:, 1], vb), edges,
+                                               estimator=estimator, edge_rule="left")
+    assert np.array_equal(cnt, cnt_w)
+    for k in range(len(edges)):
+        x = df2[(d >= lo[k]) & (d < edges[k])]
+        if x.size == 0:
+            continue
+        want = {"matheron": np.sum(x**2), "cressie": np.sum(np.sqrt(x)), "dowd": np.median(x)}[estimator]
+        assert third[k] == pytest.approx(want, rel=2e-6 if estimator == "dowd" else 1e-12)
+
+
+def test_cdist_pair_deduplication_and_samplers() -> None:
+    """A x B with shared samples: a sample is never paired with itself and a pair of two shared samples counts once;
+    cdist_point / cdist_equidistant / pdist_ring / pdist_disk and the 1-D values + coords input run end to end."""
+    from xdem_b200 import spatialstats as xs
+
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(0, 50, (40, 2))
+    v = rng.normal(size=40)
+    ia, ib = np.arange(0, 25), np.arange(15, 40)  # samples 15..24 are in both sets
+    edges = np.array([1000.0])
+    _, cnt, ssq = xs.pairwise_lag_binning_xy(
+        xs.PairSet(pts[ia, 0], pts[ia, 1], v[ia], pts[ib, 0], pts[ib, 1], v[ib], ida=ia, idb=ib), edges)
+    pairs = {(min(i, j), max(i, j)) for i in ia for j in ib if i != j}
+    assert int(cnt[0]) == len(pairs)
+    assert ssq[0] == pytest.approx(sum((v[i] - v[j]) ** 2 for i, j in pairs), rel=1e-12)
+
+    vals, _ = _sample((120, 150), 10, 9, nan_frac=0.02)
+    for method in ("cdist_equidistant", "cdist_point", "pdist_ring", "pdist_disk", "pdist_point"):
+        for est in ("matheron", "dowd"):
+            df = xs.sample_empirical_variogram(vals, gsd=2.0, subsample=200, subsample_method=method, estimator=est,
+                                               random_state=3)
+            assert list(df.columns) == ["exp", "lags", "count", "err_exp"] and df["count"].sum() > 0, (method, est)
+            ok = df["count"] > 0
+            assert np.isfinite(df["exp"][ok]).all() and (df["exp"][ok] >= 0).all()
+    # white noise of unit variance: every well-populated lag class has a semivariance near 1 with the default sampler
+    df = xs.sample_empirical_variogram(vals, gsd=2.0, subsample=2000, random_state=1)
+    big = df["count"] > 2000
+    assert big.any() and np.allclose(df["exp"][big], 1.0, atol=0.15)
+    # 1-D values + coords == the same samples passed as a grid (pdist_point with every valid sample drawn)
+    small = vals[:20, :30].copy()
+    gx, gy = np.meshgrid(np.arange(0, 20 * 2.0, 2.0), np.arange(0, 30 * 2.0, 2.0))
+    coords = np.dstack((gx.flatten(), gy.flatten())).squeeze()
+    bf = [2.0, 4.0, 7.5, 15.0, 33.3, 80.0]
+    d1 = xs.sample_empirical_variogram(small.flatten(), coords=coords, subsample=10**6, subsample_method="pdist_point",
+                                       random_state=2, bin_func=bf)
+    d2 = xs.sample_empirical_variogram(small, gsd=2.0, subsample=10**6, subsample_method="pdist_point", random_state=2,
+                                       bin_func=bf)
+    assert np.array_equal(d1["count"].values, d2["count"].values)
+    assert np.allclose(d1["exp"].values, d2["exp"].values, rtol=1e-5, equal_nan=True)
+    assert np.allclose(d1["lags"].values, d2["lags"].values)
 
 
 def test_variogram_large_properties() -> None:

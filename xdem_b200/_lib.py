@@ -60,6 +60,10 @@ def lib() -> ctypes.CDLL:
                                            c_int, c_void_p, c_uint32, c_int, c_void_p, c_void_p, c_void_p]
     L.xb_variogram_maxd2.restype = c_int
     L.xb_variogram_maxd2.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
+    L.xb_variogram_pairs_xy.restype = c_int
+    L.xb_variogram_pairs_xy.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
+                                        c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.xb_nk_aux.restype = c_int
     L.xb_nk_aux.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p,
                             c_int64, c_void_p]
@@ -126,6 +130,6 @@ EXPORTED = ["xb_last_error", "xb_version", "xb_launch_count", "xb_terrain_fused"
             "xb_nk_dh", "xb_nk_hist", "xb_nk_next", "xb_nk_make_keys", "xb_nk_hist_keys", "xb_nk_next_keys",
             "xb_windowed_generic", "xb_set_option", "xb_shift_resample", "xb_texture_prepare", "xb_texture_filter",
             "xb_texture_finish", "xb_bin_keys", "xb_bin_hist", "xb_bin_next", "xb_bin_absdev_keys", "xb_probe_stream", "xb_probe_exact_math",
-            "xb_terrain_fused_host_rows", "xb_release_scratch"]
+            "xb_terrain_fused_host_rows", "xb_release_scratch", "xb_variogram_pairs_xy"]
 
 __all__ = ["lib", "check", "launch_count", "set_option", "XdemB200Error", "LIB_PATH", "EXPORTED"]

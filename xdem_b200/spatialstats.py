@@ -10,8 +10,10 @@ states (:1469-1478), aggregation over runs (:1512-1527), last bin dropped (:1541
 from __future__ import annotations
 
 import ctypes
+import logging
 import math
 import os
+import warnings
 from fractions import Fraction
 from typing import Any, Iterable
 
@@ -240,6 +242,164 @@ def pairwise_lag_binning(x: torch.Tensor, y: torch.Tensor, v: torch.Tensor, edge
     return edges, count_h, median
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# general float64 coordinates (1-D values + coords, non-dyadic gsd, the cdist samplers)
+# ---------------------------------------------------------------------------------------------------------------
+
+
+def d2_thresholds(edges: Iterable[float], rule: str | None = None) -> np.ndarray:
+    """float64 thresholds on the squared distance: rule "left": T = min{t : sqrt(t) >= edge}, so that
+    sqrt(d2) < edge <=> d2 < T; rule "right": T = min{t : sqrt(t) > edge} (sqrt(d2) <= edge <=> d2 < T).  sqrt is the
+    correctly rounded IEEE square root scipy / cKDTree take, and it is monotone, so the comparison on d2 is exact."""
+    rule = rule or LAG_EDGE_RULE
+    if rule not in ("left", "right"):
+        raise ValueError(f"lag edge rule must be 'left' or 'right', got {rule!r}")
+    out = []
+    for e in edges:
+        e = float(e)
+        if not e > 0:
+            out.append(0.0 if rule == "left" else float(np.nextafter(0.0, 1.0)))
+            continue
+        if not math.isfinite(e):
+            out.append(math.inf)
+            continue
+        t = e * e
+        if rule == "left":
+            while t > 0 and math.sqrt(np.nextafter(t, 0.0)) >= e:
+                t = float(np.nextafter(t, 0.0))
+            while math.sqrt(t) < e:
+                t = float(np.nextafter(t, math.inf))
+        else:
+            while t > 0 and math.sqrt(np.nextafter(t, 0.0)) > e:
+                t = float(np.nextafter(t, 0.0))
+            while math.sqrt(t) <= e:
+                t = float(np.nextafter(t, math.inf))
+        out.append(t)
+    return np.asarray(out, dtype=np.float64)
+
+
+def _f64(a: Any, dev: torch.device) -> torch.Tensor:
+    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64)))
+    return t.to(device=dev, dtype=torch.float64).contiguous()
+
+
+def _morton_order_xy(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """Order along a space-filling curve (16-bit quantised coordinates): consecutive samples are close in space, so a
+    thread's consecutive pairs mostly fall in the same lag class (the kernel's run-length cache)."""
+    def q(v: torch.Tensor) -> torch.Tensor:
+        lo, hi = v.min(), v.max()
+        span = torch.clamp(hi - lo, min=1e-300)
+        return ((v - lo) / span * 65535.0).to(torch.int64)
+
+    return torch.argsort(_spread_bits16(q(x)) | (_spread_bits16(q(y)) << 1))
+
+
+#: per-pair output of the Dowd path: 6 bytes per slot of the (na x nb) rectangles
+_MAX_PAIR_SLOTS = 1_500_000_000
+
+
+class PairSet:
+    """One block of pairs for ``pairwise_lag_binning_xy``: all pairs i < j of set A (``xb is None``) or all pairs between
+    A and B.  ``ida`` / ``idb`` (optional, A x B): identities of the samples -- a pair of a sample with itself is skipped
+    and a pair whose samples both occur in BOTH sets is counted once."""
+
+    def __init__(self, xa: Any, ya: Any, va: Any, xb: Any = None, yb: Any = None, vb: Any = None, ida: Any = None,
+                 idb: Any = None) -> None:
+        dev = _arrays.require_cuda()
+        self.dev = dev
+        xa, ya, va = _f64(xa, dev), _f64(ya, dev), _f64(va, dev)
+        oa = _morton_order_xy(xa, ya) if xa.numel() > 1 else torch.zeros(xa.numel(), dtype=torch.int64, device=dev)
+        self.xa, self.ya, self.va = xa[oa].contiguous(), ya[oa].contiguous(), va[oa].contiguous()
+        self.two = xb is not None
+        self.ida = self.idb = self.dupa = self.dupb = None
+        if self.two:
+            xb, yb, vb = _f64(xb, dev), _f64(yb, dev), _f64(vb, dev)
+            ob = _morton_order_xy(xb, yb) if xb.numel() > 1 else torch.zeros(xb.numel(), dtype=torch.int64, device=dev)
+            self.xb, self.yb, self.vb = xb[ob].contiguous(), yb[ob].contiguous(), vb[ob].contiguous()
+            if ida is not None and idb is not None:
+                ia = torch.as_tensor(np.asarray(ida), dtype=torch.int64).to(dev)[oa].contiguous()
+                ib = torch.as_tensor(np.asarray(idb), dtype=torch.int64).to(dev)[ob].contiguous()
+                self.ida, self.idb = ia, ib
+                self.dupa = torch.isin(ia, ib).to(torch.uint8).contiguous()
+                self.dupb = torch.isin(ib, ia).to(torch.uint8).contiguous()
+        self.na = int(self.xa.numel())
+        self.nb = int(self.xb.numel()) if self.two else 0
+
+    @property
+    def slots(self) -> int:
+        return self.na * (self.nb if self.two else self.na)
+
+    def run(self, thr: torch.Tensor, est: int, count: Any = None, total: Any = None, maxbits: Any = None,
+            pcls: Any = None, pkey: Any = None) -> None:
+        L = _lib.lib()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+        def ptr(t: Any) -> Any:
+            return t.data_ptr() if t is not None else None
+
+        with torch.cuda.device(self.dev):
+            _lib.check(L.xb_variogram_pairs_xy(
+                self.xa.data_ptr(), self.ya.data_ptr(), self.va.data_ptr(), self.na,
+                ptr(self.xb) if self.two else None, ptr(self.yb) if self.two else None,
+                ptr(self.vb) if self.two else None, self.nb, thr.data_ptr(), int(thr.numel()), est, ptr(count),
+                ptr(total), ptr(maxbits), ptr(pcls), ptr(pkey), ptr(self.ida), ptr(self.idb), ptr(self.dupa),
+                ptr(self.dupb), stream))
+
+
+def pairwise_lag_binning_xy(sets: "PairSet | list[PairSet]", edges: Any = None, n_lags: int | None = None,
+                            maxlag: float | None = None, estimator: str = "matheron", edge_rule: str | None = None
+                            ) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Pair binning for arbitrary float64 coordinates (xb_variogram_pairs_xy), accumulated over one or more blocks of
+    pairs (e.g. the runs of the equidistant sampler).  Same return convention as ``pairwise_lag_binning``."""
+    from . import binning
+
+    if estimator not in ("matheron", "cressie", "dowd"):
+        raise NotImplementedError(f"estimator '{estimator}'")
+    sets = [sets] if isinstance(sets, PairSet) else [s for s in sets if s.na > 0 and (not s.two or s.nb > 0)]
+    if not sets:
+        raise ValueError("no sample pairs")
+    dev = sets[0].dev
+    if edges is None:
+        # skgstat.binning.even_width_lags: n_lags classes over [0, min(maxlag, largest distance)]
+        mb = torch.zeros(1, dtype=torch.int64, device=dev)
+        c0 = torch.zeros(1, dtype=torch.int64, device=dev)
+        s0 = torch.zeros(1, dtype=torch.float64, device=dev)
+        t0 = torch.zeros(1, dtype=torch.float64, device=dev)
+        for ps in sets:
+            ps.run(t0, 0, c0, s0, mb)
+        dmax = math.sqrt(float(mb.view(torch.float64).item()))
+        top = dmax if (maxlag is None or maxlag > dmax) else float(maxlag)
+        edges = np.linspace(0, top, int(n_lags) + 1)[1:]
+    edges = np.asarray(list(edges), dtype=np.float64)
+    thr_h = d2_thresholds(edges, edge_rule)
+    if not np.all(np.diff(thr_h) >= 0):
+        raise ValueError("bin edges must be ascending")
+    thr = torch.from_numpy(thr_h).to(dev)
+    nbins = len(edges)
+    count = torch.zeros(nbins, dtype=torch.int64, device=dev)
+    total = torch.zeros(nbins, dtype=torch.float64, device=dev)
+    for ps in sets:
+        ps.run(thr, 1 if estimator == "cressie" else 0, count, total)
+    count_h = count.cpu().numpy()
+    if estimator != "dowd":
+        return edges, count_h, total.cpu().numpy()
+    slots = sum(ps.slots for ps in sets)
+    if slots > _MAX_PAIR_SLOTS:
+        raise NotImplementedError(
+            f"Dowd's estimator on general coordinates materialises one (class, key) slot per pair: {slots:.3g} slots "
+            f"exceed the {_MAX_PAIR_SLOTS:.3g} limit; use grid samples (2-D values + exact gsd) or fewer samples")
+    pcls = torch.empty(slots, dtype=torch.int16, device=dev)
+    pkey = torch.empty(slots, dtype=torch.int32, device=dev)
+    o = 0
+    for ps in sets:
+        ps.run(thr, 2, pcls=pcls[o:o + ps.slots], pkey=pkey[o:o + ps.slots])
+        o += ps.slots
+    med, cnt2 = binning._select_medians(pkey, pcls, nbins)
+    if not np.array_equal(cnt2, count_h):
+        raise _lib.XdemB200Error("internal error: per-pair classes disagree with the class counts")
+    return edges, count_h, med.astype(np.float64)
+
+
 def estimate_from_sums(count: np.ndarray, third: np.ndarray, estimator: str) -> np.ndarray:
     """skgstat.estimators (1.0.x): matheron = sum d^2 / (2n); cressie = (mean |d|^0.5)^4 / (2 (0.457 + 0.494/n +
     0.045/n^2)); dowd = 2.198 median(|d|)^2 / 2.  NaN for empty classes."""
@@ -252,6 +412,286 @@ def estimate_from_sums(count: np.ndarray, third: np.ndarray, estimator: str) -> 
         else:
             exp = 2.198 * third**2 / 2.0
     return np.where(count > 0, exp, np.nan)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# samplers (host-side integer geometry / index draws; the pair work goes to the kernels)
+# ---------------------------------------------------------------------------------------------------------------
+
+
+def gsd_is_exact(gsd: float, n: int) -> bool:
+    """True if index*gsd, its differences, their squares and the sum of two squares are all exact in float64 for
+    indices below n -- then the reference's float64 distances only depend on the integer squared pixel distance and the
+    integer kernel reproduces its classes exactly.  (gsd = m * 2^e with m odd: needs 2 (bits(m) + bits(n)) + 1 <= 53.)"""
+    m, _ = float(gsd).as_integer_ratio()
+    while m % 2 == 0 and m:
+        m //= 2
+    return 2 * (int(abs(m)).bit_length() + int(max(n, 1)).bit_length()) + 1 <= 53
+
+
+class _GridSamples:
+    """Samples of a 2-D array with implicit coordinates (spatialstats.py:1413-1416: x over shape[0], y over shape[1],
+    flattened row-major -- flat sample k sits at pixel (k % nx, k // nx)); nothing of the raster's size is materialised."""
+
+    def __init__(self, values2d: torch.Tensor, gsd: float) -> None:
+        self.t = values2d
+        self.flat = values2d.reshape(-1)
+        self.nx, self.ny = int(values2d.shape[0]), int(values2d.shape[1])
+        self.gsd = float(gsd)
+        self.n = self.nx * self.ny
+        self._n_valid: int | None = None
+
+    @property
+    def n_valid(self) -> int:
+        if self._n_valid is None:
+            self._n_valid = int(torch.isfinite(self.flat).sum().item())
+        return self._n_valid
+
+    def extent(self) -> tuple[float, float, float, float]:
+        xs = np.arange(0, self.nx * self.gsd, self.gsd)
+        ys = np.arange(0, self.ny * self.gsd, self.gsd)
+        return float(xs.min()), float(xs.max()), float(ys.min()), float(ys.max())
+
+    def pix(self, idx: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+        return idx % self.nx, idx // self.nx
+
+    def xyv(self, idx: np.ndarray) -> tuple[np.ndarray, np.ndarray, torch.Tensor]:
+        px, py = self.pix(idx)
+        v = self.flat[torch.from_numpy(np.asarray(idx, dtype=np.int64)).to(self.flat.device)].to(torch.float64)
+        return px * self.gsd, py * self.gsd, v  # np.arange(0, n*gsd, gsd)[i] == i*gsd in float64
+
+    def finite(self, idx: np.ndarray) -> np.ndarray:
+        if idx.size == 0:
+            return np.zeros(0, dtype=bool)
+        t = torch.from_numpy(np.asarray(idx, dtype=np.int64)).to(self.flat.device)
+        return torch.isfinite(self.flat[t]).cpu().numpy()
+
+    def draw_valid(self, k: int, rng: np.random.Generator) -> np.ndarray:
+        return _draw_valid_subsample(self.flat, int(k), rng).cpu().numpy()
+
+    def ring(self, cx: float, cy: float, r_in: float, r_out: float, k: int, rng: np.random.Generator) -> np.ndarray:
+        """Up to k distinct valid samples with r_in <= distance to (cx, cy) < r_out (pixel units), uniformly at random
+        without replacement.  Small rings are enumerated exactly; large ones use rejection sampling."""
+        x0, x1 = max(0, int(math.floor(cx - r_out))), min(self.nx - 1, int(math.ceil(cx + r_out)))
+        y0, y1 = max(0, int(math.floor(cy - r_out))), min(self.ny - 1, int(math.ceil(cy + r_out)))
+        if x1 < x0 or y1 < y0 or k <= 0:
+            return np.zeros(0, dtype=np.int64)
+        box = (x1 - x0 + 1) * (y1 - y0 + 1)
+        if box <= 262144:
+            yy, xx = np.mgrid[y0:y1 + 1, x0:x1 + 1]
+            d = np.sqrt((xx - cx) ** 2.0 + (yy - cy) ** 2.0)
+            sel = (d >= r_in) & (d < r_out)
+            idx = (yy[sel] * self.nx + xx[sel]).astype(np.int64)
+            idx = idx[self.finite(idx)]
+            if idx.size <= k:
+                return idx
+            return idx[rng.choice(idx.size, size=k, replace=False)]
+        got = np.zeros(0, dtype=np.int64)
+        for _ in range(64):
+            m = max(4 * (k - got.size), 64)
+            xx = rng.integers(x0, x1 + 1, size=m)
+            yy = rng.integers(y0, y1 + 1, size=m)
+            d = np.sqrt((xx - cx) ** 2.0 + (yy - cy) ** 2.0)
+            cand = (yy * self.nx + xx)[(d >= r_in) & (d < r_out)].astype(np.int64)
+            cand = cand[self.finite(cand)]
+            allc = np.concatenate([got, cand])
+            _, first = np.unique(allc, return_index=True)
+            got = allc[np.sort(first)]
+            if got.size >= k:
+                return got[:k]
+        return got
+
+
+class _PointSamples:
+    """Samples with explicit coordinates (1-D values + ``coords``, spatialstats.py:1404-1410)."""
+
+    def __init__(self, values1d: torch.Tensor, coords: np.ndarray, gsd: float | None) -> None:
+        dev = values1d.device
+        self.flat = values1d
+        self.c = torch.from_numpy(np.ascontiguousarray(coords, dtype=np.float64)).to(dev)
+        self.n = int(values1d.numel())
+        self.gsd = gsd
+        self.nx = self.ny = None
+        self._valid: torch.Tensor | None = None
+
+    @property
+    def valid_idx(self) -> torch.Tensor:
+        if self._valid is None:
+            self._valid = torch.nonzero(torch.isfinite(self.flat)).flatten()
+        return self._valid
+
+    @property
+    def n_valid(self) -> int:
+        return int(self.valid_idx.numel())
+
+    def extent(self) -> tuple[float, float, float, float]:
+        return (float(self.c[:, 0].min()), float(self.c[:, 0].max()), float(self.c[:, 1].min()),
+                float(self.c[:, 1].max()))
+
+    def xyv(self, idx: np.ndarray) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        t = torch.from_numpy(np.asarray(idx, dtype=np.int64)).to(self.flat.device)
+        return self.c[t, 0], self.c[t, 1], self.flat[t].to(torch.float64)
+
+    def draw_valid(self, k: int, rng: np.random.Generator) -> np.ndarray:
+        nv = self.n_valid
+        if nv == 0:
+            raise ValueError("No valid (finite) values to sample.")
+        pick = rng.choice(nv, size=min(int(k), nv), replace=False)
+        return self.valid_idx[torch.from_numpy(np.asarray(pick, dtype=np.int64)).to(self.flat.device)].cpu().numpy()
+
+    def ring_xy(self, cx: float, cy: float, r_in: float, r_out: float, k: int, rng: np.random.Generator) -> np.ndarray:
+        """Same as ``_GridSamples.ring`` with the radii in coordinate units."""
+        v = self.valid_idx
+        d = torch.sqrt((self.c[v, 0] - cx) ** 2 + (self.c[v, 1] - cy) ** 2)
+        idx = v[(d >= r_in) & (d < r_out)].cpu().numpy()
+        if idx.size <= k:
+            return idx
+        return idx[rng.choice(idx.size, size=int(k), replace=False)]
+
+
+def _choose_cdist_equidistant_sampling_parameters(**kwargs: Any) -> tuple[int, int, float]:
+    """spatialstats.py:1104-1183 (the reference's own glue): split ``subsample`` N0 into R runs of N samples per disk /
+    ring so that R * X * N^2 ~ N0^2 / 2 with X = 10 rings, and the ratio that makes the ring count exactly X."""
+    extent, shape, subsample = kwargs["extent"], kwargs["shape"], kwargs["subsample"]
+    nb_rings = kwargs["nb_rings"] if "nb_rings" in kwargs else 10
+    min_subsample = np.ceil(np.sqrt(2 * nb_rings * 2**2) + 1)
+    if subsample < min_subsample:
+        raise ValueError(f"The number of subsamples needs to be at least {min_subsample:.0f}.")
+    pairwise_comp_per_disk = np.ceil(subsample**2 / (2 * nb_rings))
+    if pairwise_comp_per_disk < 10:
+        runs = int(pairwise_comp_per_disk / 2**2)
+    else:
+        runs = int(min(100, 10 * np.ceil((pairwise_comp_per_disk / (2**2 * 10)) ** (1 / 3))))
+    subsample_per_disk_per_run = int(np.ceil(np.sqrt(pairwise_comp_per_disk / runs)))
+    maxdist = np.sqrt((extent[1] - extent[0]) ** 2 + (extent[3] - extent[2]) ** 2)
+    res = np.mean([(extent[1] - extent[0]) / (shape[0] - 1), (extent[3] - extent[2]) / (shape[1] - 1)])
+    ratio_subsample = res**2 * subsample_per_disk_per_run / (np.pi * maxdist**2 / np.sqrt(2) ** (2 * nb_rings))
+    logging.info(
+        "Equidistant circular sampling will be performed for %d runs (random center points) with pairwise "
+        "comparison between %d samples (points) of the central disk and again %d samples times %d independent "
+        "rings centered on the same center point. This results in approximately %d pairwise comparisons (duplicate "
+        "pairwise points randomly selected will be removed).",
+        runs, subsample_per_disk_per_run, subsample_per_disk_per_run, nb_rings,
+        runs * subsample_per_disk_per_run**2 * nb_rings)
+    return runs, subsample_per_disk_per_run, ratio_subsample
+
+
+def _equidistant_pair_sets(src: Any, shape: tuple[int, int], extent: tuple[float, float, float, float], samples: int,
+                           ratio_subsample: float, runs: int | None, rng: np.random.Generator,
+                           max_dist: float | None = None, center_radius: float | None = None,
+                           exp_increase_fac: float = float(np.sqrt(2))) -> list[PairSet]:
+    """Restatement of scikit-gstat's ``RasterEquidistantMetricSpace`` (third-party, UNPINNED): ``runs`` random centres;
+    per centre ``samples`` points of the disk of radius ``center_radius`` (default: the disk that holds
+    samples / ratio_subsample pixels) are paired with ``samples`` points of each ring [r_i, r_i+1), radii 0,
+    center_radius * fac^k ..., max_dist.  Returns one PairSet (disk sample x ring samples) per run."""
+    res = float(np.mean([(extent[1] - extent[0]) / (shape[0] - 1), (extent[3] - extent[2]) / (shape[1] - 1)]))
+    if max_dist is None:
+        max_dist = float(np.sqrt((extent[1] - extent[0]) ** 2 + (extent[3] - extent[2]) ** 2))
+    if runs is None:
+        runs = int((shape[0] * shape[1]) / samples * 1 / 100.0)
+    if center_radius is None:
+        center_radius = float(np.sqrt(1.0 / ratio_subsample * samples / np.pi) * res)
+    radii = [0.0]
+    r = center_radius
+    while r < max_dist:
+        radii.append(r)
+        r *= exp_increase_fac
+    radii.append(max_dist)
+    centers = src.draw_valid(min(int(runs), src.n_valid), rng)
+    grid = isinstance(src, _GridSamples)
+    sets = []
+    for c in centers:
+        if grid:
+            cpx, cpy = src.pix(np.asarray([c]))
+            cx, cy, scale = float(cpx[0]), float(cpy[0]), 1.0 / src.gsd
+            disk = src.ring(cx, cy, 0.0, center_radius * scale, samples, rng)
+            rings = [src.ring(cx, cy, radii[i] * scale, radii[i + 1] * scale, samples, rng)
+                     for i in range(len(radii) - 1)]
+        else:
+            x_, y_, _ = src.xyv(np.asarray([c]))
+            cx, cy = float(x_[0]), float(y_[0])
+            disk = src.ring_xy(cx, cy, 0.0, center_radius, samples, rng)
+            rings = [src.ring_xy(cx, cy, radii[i], radii[i + 1], samples, rng) for i in range(len(radii) - 1)]
+        eq = np.concatenate(rings) if rings else np.zeros(0, dtype=np.int64)
+        if disk.size == 0 or eq.size == 0:
+            continue
+        xa, ya, va = src.xyv(disk)
+        xb, yb, vb = src.xyv(eq)
+        sets.append(PairSet(xa, ya, va, xb, yb, vb, ida=disk, idb=eq))
+    return sets
+
+
+def _variogram_frame(sets: "PairSet | list[PairSet]", kwargs: dict[str, Any]) -> pd.DataFrame:
+    """skgstat.Variogram(...).get_empirical() / .bin_count for the given pairs: DataFrame(exp, bins, count)."""
+    estimator = kwargs.get("estimator", "matheron")
+    if estimator not in ("matheron", "cressie", "dowd"):
+        raise NotImplementedError(f"estimator='{estimator}' is not on the B200 hot path (matheron, cressie, dowd)")
+    bin_func = kwargs.get("bin_func", "even")
+    if isinstance(bin_func, str):
+        if bin_func != "even":
+            raise NotImplementedError(f"bin_func='{bin_func}' is not supported on the B200 path (use 'even' or edges)")
+        edges_in = None
+    else:
+        edges_in = np.asarray(list(bin_func), dtype=np.float64)
+    edges, count, third = pairwise_lag_binning_xy(sets, edges_in, n_lags=int(kwargs.get("n_lags", 10)),
+                                                  maxlag=kwargs.get("maxlag"), estimator=estimator)
+    return pd.DataFrame().assign(exp=estimate_from_sums(count, third, estimator), bins=edges, count=count)
+
+
+_VARIOGRAM_KW = {"estimator", "bin_func", "n_lags", "maxlag", "model", "dist_func", "use_nugget", "fit_sigma",
+                 "fit_bounds", "verbose", "samples", "binning_random_state", "binning_agg_func"}
+_METRIC_KW = {"samples", "ratio_subsample", "runs", "n_jobs", "exp_increase_fac", "center_radius", "max_dist",
+              "dist_metric", "verbose", "rnd", "shape", "extent"}
+
+
+def _get_pdist_empirical_variogram(values: Any, coords: Any, **kwargs: Any) -> pd.DataFrame:
+    """Drop-in for ``xdem.spatialstats._get_pdist_empirical_variogram`` (spatialstats.py:1064-1101): every pair of the
+    given samples, float64 coordinates, on the GPU (xb_variogram_pairs_xy).  Returns DataFrame(exp, bins, count)."""
+    kwargs.pop("random_state", None)
+    remaining = {k: v for k, v in kwargs.items() if k not in _VARIOGRAM_KW}
+    if len(remaining) != 0:
+        warnings.warn("Keyword arguments: " + ",".join(list(remaining.keys())) + " were not used.")
+    coords = np.asarray(coords, dtype=np.float64)
+    values = np.asarray(values)
+    return _variogram_frame(PairSet(coords[:, 0], coords[:, 1], values.astype(np.float64)), kwargs)
+
+
+def _get_cdist_empirical_variogram(values: Any, coords: Any, subsample_method: str, **kwargs: Any) -> pd.DataFrame:
+    """Drop-in for ``xdem.spatialstats._get_cdist_empirical_variogram`` (spatialstats.py:1186-1261): the samplers of
+    scikit-gstat's metric spaces restated (UNPINNED; the random stream is NumPy's default_rng(random_state), not
+    skgstat's) and the pair work on the GPU.  ``values`` / ``coords`` are the valid samples (1-D, (N, 2))."""
+    dev = _arrays.require_cuda()
+    v = torch.from_numpy(np.ascontiguousarray(np.asarray(values, dtype=np.float64))).to(dev)
+    src = _PointSamples(v, np.asarray(coords, dtype=np.float64), kwargs.get("gsd"))
+    return _cdist_frame(src, subsample_method, dict(kwargs))
+
+
+def _cdist_frame(src: Any, subsample_method: str, kwargs: dict[str, Any]) -> pd.DataFrame:
+    if subsample_method == "cdist_equidistant":
+        if "runs" not in kwargs and "samples" not in kwargs:
+            runs, samples, ratio_subsample = _choose_cdist_equidistant_sampling_parameters(**kwargs)
+            kwargs["ratio_subsample"], kwargs["runs"], kwargs["samples"] = ratio_subsample, runs, samples
+        kwargs.pop("subsample", None)
+    elif subsample_method == "cdist_point":
+        kwargs["samples"] = kwargs.pop("subsample")
+    rng = np.random.default_rng(kwargs.pop("random_state", None))
+    remaining = {k: v_ for k, v_ in kwargs.items() if k not in _VARIOGRAM_KW | _METRIC_KW | {"gsd", "nb_rings"}}
+    if len(remaining) != 0:
+        warnings.warn("Keyword arguments: " + ", ".join(list(remaining.keys())) + " were not used.")
+    if subsample_method == "cdist_point":
+        # skgstat.ProbabalisticMetricSpace: two independent random subsets of `samples` points, paired A x B
+        k = kwargs["samples"]
+        k = int(k) if k >= 1 else int(k * src.n_valid)
+        left, right = src.draw_valid(k, rng), src.draw_valid(k, rng)
+        xa, ya, va = src.xyv(left)
+        xb, yb, vb = src.xyv(right)
+        sets: Any = [PairSet(xa, ya, va, xb, yb, vb, ida=left, idb=right)]
+    else:
+        sets = _equidistant_pair_sets(src, kwargs["shape"], kwargs["extent"], int(kwargs["samples"]),
+                                      float(kwargs.get("ratio_subsample", 0.01)), kwargs.get("runs"), rng,
+                                      max_dist=kwargs.get("max_dist"), center_radius=kwargs.get("center_radius"),
+                                      exp_increase_fac=float(kwargs.get("exp_increase_fac", np.sqrt(2))))
+    return _variogram_frame(sets, kwargs)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -284,6 +724,24 @@ def _draw_valid_subsample(values_flat: torch.Tensor, subsample: int, rng: np.ran
     return torch.from_numpy(picked[:subsample]).to(values_flat.device)
 
 
+def _pdist_ranges(subsample_method: str, gsd: float, maxlag: float, pdist_multi_ranges: Any
+                  ) -> tuple[list[float], list[float | None]]:
+    """(inside radii, outside radii) in pixels of the successive disks / rings (spatialstats.py:1003-1038)."""
+    if subsample_method not in ("pdist_disk", "pdist_ring"):
+        return [0.0], [None]
+    if pdist_multi_ranges is None:
+        pdist_multi_ranges = []
+        new_range = gsd * 10
+        while new_range < maxlag / 2:
+            pdist_multi_ranges.append(new_range)
+            new_range *= 2
+        pdist_multi_ranges.append(maxlag)
+    binned = [0.0] + list(pdist_multi_ranges)
+    ins = [binned[i] / gsd if subsample_method == "pdist_ring" else 0.0 for i in range(len(binned) - 1)]
+    outs = [binned[i + 1] / gsd for i in range(len(binned) - 1)]
+    return ins, outs
+
+
 def sample_empirical_variogram(
     values: Any,
     gsd: float | None = None,
@@ -295,14 +753,19 @@ def sample_empirical_variogram(
     random_state: int | np.random.Generator | None = None,
     **kwargs: Any,
 ) -> pd.DataFrame:
-    """Empirical variogram (``exp``, ``lags``, ``count``, ``err_exp``) -- same signature and output frame as
-    ``xdem.spatialstats.sample_empirical_variogram``.
+    """Empirical variogram (``exp``, ``lags``, ``count``, ``err_exp``) -- same signature, defaults and output frame as
+    ``xdem.spatialstats.sample_empirical_variogram`` (spatialstats.py:1295-1546), with the pair work on the GPU.
 
-    GPU path: ``subsample_method="pdist_point"`` on a 2-D array / Raster-like / CUDA tensor with ``gsd`` (every pair of
-    the random subsample is compared).  Supported skgstat keywords: ``estimator`` in {"matheron" (default), "cressie",
-    "dowd"} (xDEM's uncertainty pipeline passes "dowd", spatialstats.py:1810), ``bin_func`` = iterable of right edges
-    (default: the reference's sqrt(2)-geometric edges) or ``"even"`` with ``n_lags``, ``maxlag``.
-    The disk / ring / equidistant samplers (scikit-gstat metric spaces) raise NotImplementedError.
+    Inputs: a 2-D array / Raster-like / CUDA tensor with ``gsd``, or 1-D values with ``coords``.  Every sampling method
+    of the reference is available: ``cdist_equidistant`` (the default: random centres, disk x equidistant rings),
+    ``cdist_point``, ``pdist_point`` (all pairs of a random subsample), ``pdist_disk`` / ``pdist_ring``.  Supported
+    skgstat keywords: ``estimator`` in {"matheron" (default), "cressie", "dowd"} (xDEM's uncertainty pipeline passes
+    "dowd", spatialstats.py:1810), ``bin_func`` = iterable of right edges (default: the reference's sqrt(2)-geometric
+    edges) or ``"even"`` with ``n_lags``, ``maxlag``; the sampler keywords ``runs``, ``samples``, ``ratio_subsample``,
+    ``nb_rings``, ``pdist_multi_ranges``.  Grid samples whose spacing is exact in binary take the integer-distance
+    kernel (exact classes, 1e6 samples in a third of a second); everything else the float64-coordinate kernel.
+    What scikit-gstat contributes in the reference (the samplers' random streams and edge conventions) is restated and
+    UNPINNED -- see DESIGN.md section 2.  ``n_jobs`` is accepted and ignored (the runs execute on the GPU in turn).
     """
     if _arrays.is_raster_like(values):
         gsd = values.res[0]
@@ -330,51 +793,48 @@ def sample_empirical_variogram(
             'The subsampling method must be one of "cdist_equidistant, "cdist_point", "pdist_point", '
             '"pdist_disk" or "pdist_ring".'
         )
-    if subsample_method != "pdist_point":
-        raise NotImplementedError(
-            f"subsample_method='{subsample_method}' relies on scikit-gstat's metric-space samplers and is not on the "
-            "B200 hot path yet (SURVEY.md section 8f rank 2); use subsample_method='pdist_point'."
+    if n_variograms > 1 and "bin_func" in kwargs and isinstance(kwargs.get("bin_func"), str):
+        warnings.warn(
+            "Using a named binning function of scikit-gstat might provide different binnings for each "
+            "independent run. To remediate that issue, pass bin_func as an Iterable of right bin edges, "
+            "(or use default bin_func)."
         )
-    if coords is not None:
-        raise NotImplementedError("the B200 variogram path takes a 2-D array + gsd (grid samples)")
     estimator = kwargs.get("estimator", "matheron")
     if estimator not in ("matheron", "cressie", "dowd"):
         raise NotImplementedError(f"estimator='{estimator}' is not on the B200 hot path (matheron, cressie, dowd)")
-    unknown = set(kwargs) - {"estimator", "bin_func", "n_lags", "maxlag"}
-    if unknown:
-        raise NotImplementedError(f"unsupported skgstat keyword(s) for the B200 variogram path: {sorted(unknown)}")
 
     dev = _arrays.require_cuda()
-    gsd = float(gsd)
     t = values if isinstance(values, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(values))
-    t = t.to(device=dev, dtype=torch.float32)
-    nx, ny = t.shape
-    flat = t.reshape(-1)
-
-    # coordinates of flat sample k: (k % nx, k // nx) in pixels -- np.meshgrid(x, y) with x over shape[0] and y over
-    # shape[1] flattened row-major (spatialstats.py:1413-1416; identical to (col, row) for square arrays)
-    xs_f = np.arange(0, nx * gsd, gsd)
-    ys_f = np.arange(0, ny * gsd, gsd)
-    if "maxlag" not in kwargs:
-        maxlag = float(np.sqrt((np.max(xs_f) - np.min(xs_f)) ** 2 + (np.max(ys_f) - np.min(ys_f)) ** 2))
+    if coords is not None:
+        coords = np.asarray(coords.cpu() if isinstance(coords, torch.Tensor) else coords, dtype=np.float64)
+        if coords.shape[0] == 2 and coords.shape[1] != 2:
+            coords = np.transpose(coords)
+        src: Any = _PointSamples(t.to(device=dev, dtype=torch.float64), coords, gsd)
+        nx = ny = None
+        if gsd is None:
+            # spatialstats.py:1420-1421 derives a spacing from the first coordinates; it is only used for the default
+            # bin edges.  (The reference's expression can be <= 0, which makes its edge loop spin forever: here the
+            # magnitude is taken and a zero spacing is refused.)
+            gsd = abs(float(np.mean([coords[0, 0] - coords[0, 1], coords[0, 0] - coords[1, 0]])))
+            if not gsd > 0 and "bin_func" not in kwargs:
+                raise ValueError("Could not derive a ground sampling distance from the coordinates: pass `gsd` or "
+                                 "`bin_func`.")
     else:
-        maxlag = float(kwargs["maxlag"])
-    bin_func = kwargs.get("bin_func", None)
-    n_lags = int(kwargs.get("n_lags", 10))
-    if bin_func is None:
-        edges_in: np.ndarray | None = []  # type: ignore
+        gsd = float(gsd)
+        src = _GridSamples(t.to(device=dev, dtype=torch.float32), gsd)
+        nx, ny = src.nx, src.ny
+    extent = src.extent()
+    if "maxlag" not in kwargs:
+        kwargs["maxlag"] = float(np.sqrt((extent[1] - extent[0]) ** 2 + (extent[3] - extent[2]) ** 2))
+    maxlag = float(kwargs["maxlag"])
+    if "bin_func" not in kwargs:
+        bin_func = []
         right = np.sqrt(2) * gsd
         while right < maxlag:
-            edges_in.append(right)  # type: ignore
+            bin_func.append(right)
             right *= np.sqrt(2)
-        edges_in.append(maxlag)  # type: ignore
-        edges_in = np.asarray(edges_in, dtype=np.float64)
-    elif isinstance(bin_func, str):
-        if bin_func != "even":
-            raise NotImplementedError(f"bin_func='{bin_func}' is not supported on the B200 path (use 'even' or edges)")
-        edges_in = None
-    else:
-        edges_in = np.asarray(list(bin_func), dtype=np.float64)
+        bin_func.append(maxlag)
+        kwargs["bin_func"] = bin_func
 
     # child random states (spatialstats.py:1469-1478)
     if random_state is not None:
@@ -383,17 +843,43 @@ def sample_empirical_variogram(
     else:
         list_random_state = [None for _ in range(n_variograms)]
 
+    grid_exact = isinstance(src, _GridSamples) and gsd_is_exact(gsd, max(src.nx, src.ny))
     runs = []
     for i in range(n_variograms):
-        run_rng = np.random.default_rng(list_random_state[i])
-        idx = _draw_valid_subsample(flat, int(subsample), run_rng)
-        x = idx % nx
-        y = idx // nx
-        v = flat[idx]
-        edges, count, third = pairwise_lag_binning(x, y, v, edges_in, gsd, n_lags=n_lags, maxlag=maxlag,
-                                                   estimator=estimator)
-        exp = estimate_from_sums(count, third, estimator)
-        runs.append(pd.DataFrame().assign(exp=exp, bins=edges, count=count))
+        kw = dict(kwargs)
+        if "cdist" in subsample_method:
+            kw.update(subsample=subsample, random_state=list_random_state[i])
+            if subsample_method == "cdist_equidistant":
+                kw.update(shape=(nx, ny), extent=extent)
+            runs.append(_cdist_frame(src, subsample_method, kw))
+            continue
+        # pdist methods: xdem's own subsampling (spatialstats.py:942-1060), then all pairs of the subsample
+        multi = kw.pop("pdist_multi_ranges", None)
+        ins, outs = _pdist_ranges(subsample_method, gsd, maxlag, multi)
+        for r_in, r_out in zip(ins, outs):
+            run_rng = np.random.default_rng(list_random_state[i])
+            if r_out is None:
+                idx = src.draw_valid(int(subsample), run_rng)
+            else:
+                # random centre pixel; the mask compares the SECOND-axis index with center_x (spatialstats.py:899-901)
+                cx, cy = run_rng.choice(nx, 1)[0], run_rng.choice(ny, 1)[0]
+                idx = _ring_of_flattened_array(src, float(cx), float(cy), r_in, r_out, int(subsample), run_rng)
+            if idx.size == 0:
+                continue
+            if grid_exact:
+                ti = torch.from_numpy(np.asarray(idx, dtype=np.int64)).to(dev)
+                x, y = ti % src.nx, ti // src.nx
+                edges_in = None if isinstance(kw["bin_func"], str) else np.asarray(list(kw["bin_func"]), np.float64)
+                if isinstance(kw["bin_func"], str) and kw["bin_func"] != "even":
+                    raise NotImplementedError(f"bin_func='{kw['bin_func']}' is not supported on the B200 path")
+                edges, count, third = pairwise_lag_binning(x, y, src.flat[ti], edges_in, gsd,
+                                                           n_lags=int(kw.get("n_lags", 10)), maxlag=maxlag,
+                                                           estimator=estimator)
+                runs.append(pd.DataFrame().assign(exp=estimate_from_sums(count, third, estimator), bins=edges,
+                                                  count=count))
+            else:
+                xa, ya, va = src.xyv(idx)
+                runs.append(_variogram_frame(PairSet(xa, ya, va), kw))
 
     df = pd.concat(runs)
     if n_variograms == 1:
@@ -411,3 +897,37 @@ def sample_empirical_variogram(
     df.drop(df.tail(1).index, inplace=True)  # spatialstats.py:1541
     df = df.astype({"exp": "float64", "err_exp": "float64", "lags": "float64", "count": "int64"})
     return df
+
+
+def _ring_of_flattened_array(src: "_GridSamples", cx: float, cy: float, r_in: float, r_out: float, k: int,
+                             rng: np.random.Generator) -> np.ndarray:
+    """Flat indices of up to k valid cells of the ring / disk mask of ``_create_ring_mask`` / ``_create_circular_mask``
+    (spatialstats.py:880-939): the mask has the array's shape (nx, ny), cell (i, j) is inside iff
+    r_in <= sqrt((j - cx)^2 + (i - cy)^2) < r_out, and it is flattened row-major like the values (flat = i*ny + j)."""
+    i0, i1 = max(0, int(math.floor(cy - r_out))), min(src.nx - 1, int(math.ceil(cy + r_out)))
+    j0, j1 = max(0, int(math.floor(cx - r_out))), min(src.ny - 1, int(math.ceil(cx + r_out)))
+    if i1 < i0 or j1 < j0:
+        return np.zeros(0, dtype=np.int64)
+    got = np.zeros(0, dtype=np.int64)
+    exact = (i1 - i0 + 1) * (j1 - j0 + 1) <= 262144
+    for _ in range(1 if exact else 64):
+        if exact:
+            ii, jj = np.mgrid[i0:i1 + 1, j0:j1 + 1]
+            ii, jj = ii.ravel(), jj.ravel()
+        else:
+            m = max(4 * (k - got.size), 64)
+            ii, jj = rng.integers(i0, i1 + 1, size=m), rng.integers(j0, j1 + 1, size=m)
+        d = np.sqrt((jj - cx) ** 2.0 + (ii - cy) ** 2.0)
+        sel = (d < r_out) & ~(d < r_in)
+        cand = (ii[sel] * src.ny + jj[sel]).astype(np.int64)
+        cand = cand[src.finite(cand)]
+        allc = np.concatenate([got, cand])
+        _, first = np.unique(allc, return_index=True)
+        got = allc[np.sort(first)]
+        if exact:
+            if got.size > k:
+                got = got[rng.choice(got.size, size=k, replace=False)]
+            return got
+        if got.size >= k:
+            return got[:k]
+    return got
