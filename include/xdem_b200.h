@@ -285,6 +285,63 @@ int xb_nk_hist_keys(const uint32_t* key_dev, const uint8_t* group_dev, int64_t n
 int xb_nk_next_keys(const uint32_t* key_dev, const uint8_t* group_dev, int64_t n, int n_groups,
                     const uint32_t* sel_dev, uint32_t* next_key_dev, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Nuth & Kaab iteration with bracketed exact selection (csrc/xb_nk_fast.cu): the same exact medians as the entry points
+ * above (np.nanmedian(dh), affine.py:504; per-aspect-bin np.nanmedian of (dh - median)/slope_tan, base.py:1014-1020) from
+ * TWO streaming passes per iteration and no host round trip until the end.  Every median is first bracketed from a row
+ * sample; one full pass counts the keys below the bracket and compacts the keys inside it; a radix select on the compact
+ * buffer (ranks picked on the device) yields the exact middle values.  A bracket that misses or overflows sets a flag in
+ * cnt[C_FLAGS] and the caller repeats the iteration with the exhaustive entry points.
+ *
+ * State lives in three small device arrays whose layout xb_nkf_layout reports: out[0..15] = {MAXB, C_SIZE, K_SIZE, F_SIZE,
+ * C_NFIN, C_GBELOW, C_GNC, C_BNC, C_FLAGS, C_BTOTAL, C_BBELOW, K_ASPMIN, K_GLO, K_BLO, F_VSHIFT, F_MED};
+ *   cnt  uint64[C_SIZE]: finite-dh count, keys below the global bracket, global / per-bin compact counts, flags,
+ *        per-bin totals [C_BTOTAL + b] and below-bracket counts [C_BBELOW + b]
+ *   keys uint32[K_SIZE]: aspect min / max bit patterns, global bracket [K_GLO, K_GLO+1], per-bin brackets [K_BLO + b] /
+ *        [K_BLO + MAXB + b] (order-preserving float32 keys)
+ *   f64  double[F_SIZE]: vertical shift (median of dh), aspect range, cached range of the per-pixel bin cache,
+ *        moments {n, sum y, sum y^2} at [F_VSHIFT + 5 ..], per-bin medians [F_MED + b]
+ * Multi-GPU callers all-gather the sample / compact buffers and all-reduce the counters between the calls (segments:
+ * n_seg buffers of seg_cap slots with seg_count filled slots each).  Rasters need cols % 4 == 0 and 16-byte alignment. */
+int xb_nkf_layout(int32_t* out16);
+int xb_nkf_reset(unsigned long long* cnt_dev, uint32_t* keys_dev, double* f64_dev, uint32_t* hist_dev, void* stream);
+/* sample != 0: dh of the jittered row sample (one row of every `stride`) -> sample_dev[(rows+stride-1)/stride * cols]
+ * order-preserving keys, 0 = not finite.  sample == 0: dh of every pixel -> dh_dev, aspect range / finite count / count of
+ * keys below keys[K_GLO] into cnt / keys, keys within [K_GLO, K_GLO+1] appended to gcompact_dev (capacity gcap). */
+int xb_nkf_dh(int sample, const float* ref_dev, const float* tba_dev, const uint8_t* sub_mask_dev,
+              const float* aspect_dev, int64_t rows, int64_t cols, int64_t ld, int64_t tba_ld, int64_t tba_row0,
+              int64_t tba_rows_total, double dx_px, double dy_px, float* dh_dev, uint32_t* sample_dev, int stride,
+              uint32_t seed, unsigned long long* cnt_dev, uint32_t* keys_dev, uint32_t* gcompact_dev, uint64_t gcap,
+              void* stream);
+/* f64[aspect range] = float32 min / max of the aspect over finite dh (after the counters were all-reduced) */
+int xb_nkf_range(const uint32_t* keys_dev, double* f64_dev, void* stream);
+/* sample != 0: (key of y, aspect bin) of the sampled rows -> skey_dev / sgrp_dev.  sample == 0: every pixel -> per-bin
+ * totals / below-bracket counts / moments into cnt / f64, in-bracket (key, bin) pairs appended to bkey_dev / bgrp_dev. */
+int xb_nkf_y(int sample, const float* dh_dev, const float* slope_tan_dev, const float* aspect_dev, uint8_t* bin_cache_dev,
+             int64_t rows, int64_t cols, int n_bins, uint32_t* skey_dev, uint8_t* sgrp_dev, int stride, uint32_t seed,
+             unsigned long long* cnt_dev, const uint32_t* keys_dev, double* f64_dev, uint32_t* bkey_dev,
+             uint8_t* bgrp_dev, uint64_t bcap, void* stream);
+/* Two order statistics per group of a small key buffer by 4 x (digit histogram + device-side digit pick).  mode 0: the
+ * bracket keys around the sample median of each group -> out_lo_dev / out_hi_dev; mode 1: the exact median of the
+ * population (ext_total elements, ext_below below the bracket) from the compact buffer -> out_val_dev (mean of the two
+ * middle float32 values in float64, NaN for an empty group); a rank outside the buffer sets miss_bit in flags_dev[0]. */
+int xb_nkf_select(const uint32_t* key_dev, const uint8_t* grp_dev, int64_t n_seg, int64_t seg_cap,
+                  const unsigned long long* seg_count_dev, int64_t seg_count_stride, int n_groups, int mode,
+                  const unsigned long long* ext_total_dev, const unsigned long long* ext_below_dev, uint32_t* out_lo_dev,
+                  uint32_t* out_hi_dev, double* out_val_dev, unsigned long long* flags_dev, uint64_t miss_bit,
+                  uint32_t* hist_dev, uint32_t* prefix_dev, unsigned long long* below_dev, long long* rank_dev,
+                  void* stream);
+int xb_nkf_finalize(unsigned long long* cnt_dev, double* f64_dev, uint64_t gcap, uint64_t bcap, void* stream);
+/* One whole single-GPU iteration: the calls above in order (sample_dev / sgrp_dev hold ns = 4 * ceil(rows*cols/4/stride)
+ * entries and are reused for the dh and the y sample). */
+int xb_nkf_iteration(const float* ref_dev, const float* tba_dev, const uint8_t* sub_mask_dev, const float* slope_tan_dev,
+                     const float* aspect_dev, int64_t rows, int64_t cols, int64_t ld, int64_t tba_ld, int64_t tba_row0,
+                     int64_t tba_rows_total, double dx_px, double dy_px, int n_bins, float* dh_dev, uint8_t* bin_cache_dev,
+                     uint32_t* sample_dev, uint8_t* sgrp_dev, int64_t ns, int stride, uint32_t seed,
+                     uint32_t* gcompact_dev, uint64_t gcap, uint32_t* bkey_dev, uint8_t* bgrp_dev, uint64_t bcap,
+                     unsigned long long* cnt_dev, uint32_t* keys_dev, double* f64_dev, uint32_t* hist_dev,
+                     uint32_t* prefix_dev, unsigned long long* below_dev, long long* rank_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,9 +75,37 @@ def main() -> None:
     # to the optimiser tolerance (observed 4e-7 relative at 8 GPUs), far below the 1e-3 px convergence threshold
     assert np.allclose(shard, single, rtol=1e-5, atol=1e-7), (shard, single)
     assert abs(single[0] / 5 + 0.37) < 2e-2 and abs(single[1] / 5 + 0.61) < 2e-2, single
+    # the same on a raster large enough for the bracketed-selection path (>= 2^20 pixels): samples / compact buffers are
+    # all-gathered, counters all-reduced, every rank selects on the union -> identical exact medians
+    n = 1024 * world
+    yy = torch.arange(n, device=dev, dtype=torch.float32)[:, None]
+    xx = torch.arange(2048, device=dev, dtype=torch.float32)[None, :]
+    gen = torch.Generator(device=dev).manual_seed(11)
+    ref = surf(0.0, 0.0)
+    tba = surf(0.37, -0.61) + 1.5 + 0.02 * torch.randn(tuple(ref.shape), generator=gen, device=dev)
+    tba[700:720, 100:400] = float("nan")
+    single, n_single = coreg.nuth_kaab(ref, tba, transform=tr, tolerance=0.0, max_iterations=4,
+                                       params_random={"subsample": 1.0})
+    rows = n // world
+    shard, n_shard = xbd.sharded_nuth_kaab(ref[rank * rows:(rank + 1) * rows], tba[rank * rows:(rank + 1) * rows],
+                                           transform=tr, tolerance=0.0, max_iterations=4)
+    assert n_shard == n_single, (n_shard, n_single)
+    assert np.allclose(shard, single, rtol=1e-5, atol=1e-7), (shard, single)
+    # BASELINE config 4's request (9 surface + 4 windowed planes, two specialised launches per piece) row-sharded with
+    # the halo exchange overlapped: bit-identical to the single-GPU planes
+    s9 = ["slope", "aspect", "hillshade", "profile_curvature", "tangential_curvature", "planform_curvature",
+          "flowline_curvature", "max_curvature", "min_curvature"]
+    w4 = ["topographic_position_index", "terrain_ruggedness_index", "roughness", "rugosity"]
+    rows = H // world
+    full = _engine.terrain_fused(z, 5.0, s9, w4, surface_fit="Florinsky", degrees=True, clip_hillshade=True)
+    mine = xbd.sharded_terrain_attribute(z[rank * rows:(rank + 1) * rows].contiguous(), 5.0, s9, w4,
+                                         surface_fit="Florinsky", degrees=True, clip_hillshade=True)
+    ref13 = full[:, rank * rows:(rank + 1) * rows]
+    assert torch.equal(torch.isnan(mine), torch.isnan(ref13)) and torch.equal(torch.nan_to_num(mine),
+                                                                              torch.nan_to_num(ref13)), "all-13"
     dist.barrier()
     if rank == 0:
-        print(f"dist_check_gpu OK on {world} GPUs (terrain, variogram, Nuth-Kaab {shard})")
+        print(f"dist_check_gpu OK on {world} GPUs (terrain incl. all-13, variogram, Nuth-Kaab {shard})")
     dist.destroy_process_group()
 
 

@@ -349,6 +349,59 @@ def test_nk_subsample_and_large() -> None:
     assert nkc.meta["outputs"]["random"]["subsample_final"] == 200000
 
 
+@pytest.mark.parametrize("case", ["smooth", "holes_and_ties", "subsample"])
+def test_nk_bracketed_selection_equals_exhaustive(case: str) -> None:
+    """The two-pass bracketed selection (csrc/xb_nk_fast.cu) returns EXACTLY what the exhaustive radix select returns --
+    the median of dh, the per-bin medians of y, the per-bin counts, the aspect range, n -- over several shifts, with NaN
+    holes, heavy ties (quantised elevations), an odd / even number of valid pixels and a sparse subsample; the moments
+    agree to summation order."""
+    import torch
+
+    from oracle import synth
+    from xdem_b200 import coreg
+
+    ref, tba = synth.nk_pair((1536, 2048), shift_px=(0.37, -0.61), dz=1.5, noise=0.05)
+    inl = np.ones(ref.shape, dtype=bool)
+    if case == "holes_and_ties":
+        ref, tba = np.round(ref * 4) / 4, np.round(tba * 4) / 4  # many identical dh values
+        tba[100:400, 300:900] = np.nan
+        ref[::37, ::11] = np.nan
+        inl[1000:1001, :777] = False  # flips the parity of the valid count
+    if case == "subsample":
+        inl = np.random.default_rng(1).random(ref.shape) < 0.07
+    rt, tt, it = (torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (ref.astype(np.float32),
+                                                                              tba.astype(np.float32), inl))
+    st = coreg._NKState(rt, tt, it)
+    assert st.fast_eligible(72)
+    n_fallback = 0
+    for dx, dy in ((0.0, 0.0), (0.37, -0.61), (-1.46, 2.58), (3.0, -2.0), (0.3712, -0.6093)):
+        res = st.iteration_fast(dx, dy, 72)
+        if res is None:
+            n_fallback += 1
+            print("fallback", case, dx, dy, "flags", st.fast_last_flags)
+            continue
+        lo, hi, n_fin = st.compute_dh(dx, dy)
+        med, cnt, _ = st.select_medians(0, 0.0, 0.0, 1.0, 1)
+        assert res["n_fin"] == n_fin == cnt[0] and res["lo"] == lo and res["hi"] == hi
+        assert res["vshift"] == float(med[0]), (case, dx, dy, res["vshift"], med[0])
+        med_b, cnt_b, mom = st.select_medians(1, float(med[0]), lo, hi, 72, want_moments=True)
+        assert np.array_equal(res["counts"], cnt_b), (case, dx, dy)
+        assert np.array_equal(res["median"], med_b, equal_nan=True), (case, dx, dy, np.nanmax(np.abs(res["median"] - med_b)))
+        # n exact; sum y / sum y^2 only seed the optimiser's initial guess (affine.py:384): the fast path accumulates
+        # them in float32 per thread and row before going to float64
+        assert res["moments"][0] == mom[0] and np.allclose(res["moments"], mom, rtol=1e-5, atol=1e-3 * mom[0] ** 0.5)
+    assert n_fallback == 0, "a 4-sigma bracket should not miss on these inputs"
+    # whole fits: identical offsets with and without the fast path
+    tr = (5.0, 0, 0, 0, -5.0, 0)
+    fast = coreg.nuth_kaab(rt, tt, inlier_mask=it, transform=tr, tolerance=0.0, max_iterations=4)
+    coreg.NK_FAST = False
+    try:
+        slow = coreg.nuth_kaab(rt, tt, inlier_mask=it, transform=tr, tolerance=0.0, max_iterations=4)
+    finally:
+        coreg.NK_FAST = True
+    assert fast[1] == slow[1] and np.allclose(fast[0], slow[0], rtol=1e-9, atol=1e-12), (fast, slow)
+
+
 def test_nk_apply_translation() -> None:
     """`apply`: regrid of the shifted DEM on the input grid == map_coordinates restatement; after
     applying the fitted shift the residual dh median is ~0 and a second fit finds (almost) no shift."""

@@ -85,6 +85,25 @@ def lib() -> ctypes.CDLL:
                                   c_void_p]
     L.xb_nk_next_keys.restype = c_int
     L.xb_nk_next_keys.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]
+    for name in ("xb_nkf_layout", "xb_nkf_reset", "xb_nkf_dh", "xb_nkf_range", "xb_nkf_y", "xb_nkf_select",
+                 "xb_nkf_finalize", "xb_nkf_iteration"):
+        getattr(L, name).restype = c_int
+    L.xb_nkf_layout.argtypes = [c_void_p]
+    L.xb_nkf_reset.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.xb_nkf_dh.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                            c_int64, c_double, c_double, c_void_p, c_void_p, c_int, c_uint32, c_void_p, c_void_p,
+                            c_void_p, c_uint64, c_void_p]
+    L.xb_nkf_range.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.xb_nkf_y.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p,
+                           c_int, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]
+    L.xb_nkf_select.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p]
+    L.xb_nkf_finalize.argtypes = [c_void_p, c_void_p, c_uint64, c_uint64, c_void_p]
+    L.xb_nkf_iteration.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                   c_int64, c_int64, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_int64, c_int, c_uint32, c_void_p, c_uint64, c_void_p, c_void_p, c_uint64, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.xb_texture_prepare.restype = c_int
     L.xb_texture_prepare.argtypes = [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64,
                                      c_int64, c_int, c_void_p, c_void_p]
@@ -130,6 +149,7 @@ EXPORTED = ["xb_last_error", "xb_version", "xb_launch_count", "xb_terrain_fused"
             "xb_nk_dh", "xb_nk_hist", "xb_nk_next", "xb_nk_make_keys", "xb_nk_hist_keys", "xb_nk_next_keys",
             "xb_windowed_generic", "xb_set_option", "xb_shift_resample", "xb_texture_prepare", "xb_texture_filter",
             "xb_texture_finish", "xb_bin_keys", "xb_bin_hist", "xb_bin_next", "xb_bin_absdev_keys", "xb_probe_stream", "xb_probe_exact_math",
-            "xb_terrain_fused_host_rows", "xb_release_scratch", "xb_variogram_pairs_xy"]
+            "xb_terrain_fused_host_rows", "xb_release_scratch", "xb_variogram_pairs_xy",
+            "xb_nkf_layout", "xb_nkf_reset", "xb_nkf_dh", "xb_nkf_range", "xb_nkf_y", "xb_nkf_select", "xb_nkf_finalize", "xb_nkf_iteration"]
 
 __all__ = ["lib", "check", "launch_count", "set_option", "XdemB200Error", "LIB_PATH", "EXPORTED"]

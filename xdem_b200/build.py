@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJDIR = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libxdem_b200.so")
-SOURCES = ["xb_capi.cu", "xb_terrain.cu", "xb_terrain_fl.cu", "xb_terrain_w3.cu", "xb_terrain_host.cu", "xb_variogram.cu", "xb_variogram_xy.cu", "xb_nuthkaab.cu", "xb_window_generic.cu", "xb_texture.cu", "xb_binning.cu", "xb_probe.cu"]
+SOURCES = ["xb_capi.cu", "xb_terrain.cu", "xb_terrain_fl.cu", "xb_terrain_w3.cu", "xb_terrain_host.cu", "xb_variogram.cu", "xb_variogram_xy.cu", "xb_nuthkaab.cu", "xb_nk_fast.cu", "xb_window_generic.cu", "xb_texture.cu", "xb_binning.cu", "xb_probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "-DXB_BUILDING"]
 

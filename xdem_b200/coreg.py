@@ -21,6 +21,9 @@ import torch
 
 from . import _arrays, _lib
 
+#: bracketed exact selection (csrc/xb_nk_fast.cu) for rasters of >= 2^20 pixels; False forces the exhaustive radix select
+NK_FAST = True
+
 
 def _nuth_kaab_fit_func(xx: np.ndarray, *params: float) -> np.ndarray:
     """y(x) = a * cos(b - x) + c  (affine.py:340-355)."""
@@ -148,6 +151,211 @@ class _NKState:
         below = np.where(digit > 0, cum[np.arange(n_groups), np.maximum(digit - 1, 0)], 0)
         return digit, below
 
+    # ------------------------------------------------------------------ bracketed selection (csrc/xb_nk_fast.cu)
+    def fast_eligible(self, n_bins: int) -> bool:
+        """The fast path needs vector-aligned rasters and enough pixels for sampling to pay off."""
+        import torch.distributed as dist
+
+        if not NK_FAST or n_bins > 96 or self.cols % 4 or self.ref.stride(0) % 4 or self.tba_buf.stride(0) % 4:
+            return False
+        n_global = self.n
+        if self.sharded and dist.is_available() and dist.is_initialized():
+            t = torch.tensor([self.n], dtype=torch.int64, device=self.dev)
+            dist.all_reduce(t, group=self.group)
+            n_global = int(t.item())
+        self._n_global = n_global
+        return n_global >= (1 << 20) and self.rows >= 8
+
+    def _fast_setup(self, n_bins: int) -> None:
+        import torch.distributed as dist
+
+        L, dev = self.L, self.dev
+        lay = (ctypes.c_int32 * 16)()
+        _lib.check(L.xb_nkf_layout(lay))
+        names = ["MAXB", "C_SIZE", "K_SIZE", "F_SIZE", "C_NFIN", "C_GBELOW", "C_GNC", "C_BNC", "C_FLAGS", "C_BTOTAL",
+                 "C_BBELOW", "K_ASPMIN", "K_GLO", "K_BLO", "F_VSHIFT", "F_MED"]
+        self.lay = {k: int(v) for k, v in zip(names, lay)}
+        world = dist.get_world_size(self.group) if (self.sharded and dist.is_initialized()) else 1
+        self._world = world
+        n_global = self._n_global
+        # ~8 M sampled pixels over the whole raster: one 4-pixel chunk out of every `stride`, jittered
+        self.stride = max(1, int(n_global // 8_000_000))
+        n_schunks = (self.rows * (self.cols // 4) + self.stride - 1) // self.stride
+        ns = 4 * n_schunks
+        if world > 1:
+            t = torch.tensor([ns], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            ns = int(t.item())
+        self.ns = ns
+        m = max(1.0, n_global / self.stride)  # sample size over all ranks
+        frac_g = min(1.0, 2.0 * (4.0 * np.sqrt(m) + 8.0) / m)  # bracket = +-(4 sqrt(m) + 8) sample ranks
+        mb = max(1.0, m / n_bins)
+        frac_b = min(1.0, 2.0 * (4.0 * np.sqrt(mb) + 8.0) / mb)
+        self.gcap = int(min(self.n, 3 * frac_g * self.n + 65536))
+        self.bcap = int(min(self.n, 2.5 * frac_b * self.n + 262144))
+        i32, u8, i64, f64 = torch.int32, torch.uint8, torch.int64, torch.float64
+        self.f_sample = torch.zeros(ns, dtype=i32, device=dev)       # keys (0 = empty); reused for the y sample
+        self.f_sgrp = torch.full((ns,), 255, dtype=u8, device=dev)
+        self.f_gcompact = torch.empty(self.gcap, dtype=i32, device=dev)
+        self.f_bkey = torch.empty(self.bcap, dtype=i32, device=dev)
+        self.f_bgrp = torch.empty(self.bcap, dtype=u8, device=dev)
+        self.f_bins = torch.empty(self.n, dtype=u8, device=dev)
+        self.f_cnt = torch.zeros(self.lay["C_SIZE"], dtype=i64, device=dev)
+        self.f_keys = torch.zeros(self.lay["K_SIZE"], dtype=i32, device=dev)
+        self.f_f64 = torch.full((self.lay["F_SIZE"],), float("nan"), dtype=f64, device=dev)
+        maxb = self.lay["MAXB"]
+        self.f_hist = torch.zeros(2 * maxb * 256, dtype=i32, device=dev)
+        self.f_prefix = torch.zeros(2 * maxb, dtype=i32, device=dev)
+        self.f_below = torch.zeros(2 * maxb, dtype=i64, device=dev)
+        self.f_rank = torch.zeros(2 * maxb, dtype=i64, device=dev)
+        if world > 1:
+            self.g_sample = torch.empty(world * ns, dtype=i32, device=dev)
+            self.g_sgrp = torch.empty(world * ns, dtype=u8, device=dev)
+            self.g_gcompact = torch.empty(world * self.gcap, dtype=i32, device=dev)
+            self.g_bkey = torch.empty(world * self.bcap, dtype=i32, device=dev)
+            self.g_bgrp = torch.empty(world * self.bcap, dtype=u8, device=dev)
+            self.g_counts = torch.zeros(world, dtype=i64, device=dev)
+        self._fast_ready = n_bins
+        self._fast_iter = 0
+
+    def iteration_fast(self, dx_px: float, dy_px: float, n_bins: int) -> dict[str, Any] | None:
+        """One iteration's device work on the bracketed-selection path; returns the statistics the host fit needs, or
+        None when a bracket missed / a compact buffer overflowed (the caller then takes the exhaustive path)."""
+        import torch.distributed as dist
+
+        if getattr(self, "_fast_ready", None) != n_bins:
+            self._fast_setup(n_bins)
+        if self.sharded:
+            need = int(np.ceil(abs(dy_px))) + 1
+            top, bot = self.tba_halo_rows
+            if (top and top < need) or (bot and bot < need):
+                raise ValueError(f"row shift of {dy_px:.2f} px exceeds the {min(top or bot, bot or top)}-row halo of the "
+                                 "sharded Nuth-Kaab fit; re-run with a larger `halo`")
+        L, lay, st = self.L, self.lay, self.stream
+        world, group = self._world, self.group
+        cnt, keys, f64 = self.f_cnt, self.f_keys, self.f_f64
+        self._fast_iter += 1
+        seed = (self._fast_iter * 0x9E3779B1) & 0xFFFFFFFF
+        c8 = cnt.element_size()
+
+        def cptr(i: int) -> int:
+            return cnt.data_ptr() + c8 * i
+
+        def kptr(i: int) -> int:
+            return keys.data_ptr() + 4 * i
+
+        def fptr(i: int) -> int:
+            return f64.data_ptr() + 8 * i
+
+        def dh(sample: int) -> None:
+            _lib.check(L.xb_nkf_dh(sample, self.ref.data_ptr(), self.tba_buf.data_ptr(), self.sub_mask.data_ptr(),
+                                   self.aspect.data_ptr(), self.rows, self.cols, self.ref.stride(0),
+                                   self.tba_buf.stride(0), self.tba_row0, self.tba_buf.shape[0], float(dx_px),
+                                   float(dy_px), self.dh.data_ptr(), self.f_sample.data_ptr(), self.stride, seed,
+                                   cnt.data_ptr(), keys.data_ptr(), self.f_gcompact.data_ptr(), self.gcap, st))
+
+        def yk(sample: int) -> None:
+            _lib.check(L.xb_nkf_y(sample, self.dh.data_ptr(), self.slope_tan.data_ptr(), self.aspect.data_ptr(),
+                                  self.f_bins.data_ptr(), self.rows, self.cols, n_bins, self.f_sample.data_ptr(),
+                                  self.f_sgrp.data_ptr(), self.stride, seed ^ 0x5BD1E995, cnt.data_ptr(), keys.data_ptr(),
+                                  f64.data_ptr(), self.f_bkey.data_ptr(), self.f_bgrp.data_ptr(), self.bcap, st))
+
+        def select(key: torch.Tensor, grp: torch.Tensor | None, n_seg: int, seg_cap: int, seg_count: int | None,
+                   G: int, mode: int, ext_total: int | None, ext_below: int | None, out_lo: int | None,
+                   out_hi: int | None, out_val: int | None, miss_bit: int) -> None:
+            _lib.check(L.xb_nkf_select(key.data_ptr(), grp.data_ptr() if grp is not None else None, n_seg, seg_cap,
+                                       seg_count, 1, G, mode, ext_total, ext_below, out_lo, out_hi, out_val,
+                                       cptr(lay["C_FLAGS"]), miss_bit, self.f_hist.data_ptr(),
+                                       self.f_prefix.data_ptr(), self.f_below.data_ptr(), self.f_rank.data_ptr(), st))
+
+        if world == 1:
+            with torch.cuda.device(self.dev):
+                _lib.check(L.xb_nkf_iteration(
+                    self.ref.data_ptr(), self.tba_buf.data_ptr(), self.sub_mask.data_ptr(), self.slope_tan.data_ptr(),
+                    self.aspect.data_ptr(), self.rows, self.cols, self.ref.stride(0), self.tba_buf.stride(0),
+                    self.tba_row0, self.tba_buf.shape[0], float(dx_px), float(dy_px), n_bins, self.dh.data_ptr(),
+                    self.f_bins.data_ptr(), self.f_sample.data_ptr(), self.f_sgrp.data_ptr(), self.ns, self.stride, seed,
+                    self.f_gcompact.data_ptr(), self.gcap, self.f_bkey.data_ptr(), self.f_bgrp.data_ptr(), self.bcap,
+                    cnt.data_ptr(), keys.data_ptr(), f64.data_ptr(), self.f_hist.data_ptr(), self.f_prefix.data_ptr(),
+                    self.f_below.data_ptr(), self.f_rank.data_ptr(), st))
+                cnt_h = cnt.cpu().numpy()  # the iteration's only host synchronisation
+                f_h = f64.cpu().numpy()
+            return self._fast_result(cnt_h, f_h, n_bins)
+        with torch.cuda.device(self.dev):
+            _lib.check(L.xb_nkf_reset(cnt.data_ptr(), keys.data_ptr(), f64.data_ptr(), self.f_hist.data_ptr(), st))
+            # 1-2: sample of dh -> global bracket
+            dh(1)
+            if world > 1:
+                dist.all_gather_into_tensor(self.g_sample, self.f_sample, group=group)
+                select(self.g_sample, None, 1, world * self.ns, None, 1, 0, None, None, kptr(lay["K_GLO"]),
+                       kptr(lay["K_GLO"] + 1), None, 1)
+            else:
+                select(self.f_sample, None, 1, self.ns, None, 1, 0, None, None, kptr(lay["K_GLO"]),
+                       kptr(lay["K_GLO"] + 1), None, 1)
+            # 3: the full dh pass
+            dh(0)
+            if world > 1:
+                dist.all_reduce(cnt[lay["C_NFIN"]:lay["C_GBELOW"] + 1], group=group)
+                amin = keys[lay["K_ASPMIN"]:lay["K_ASPMIN"] + 1].to(torch.int64) & 0xFFFFFFFF
+                amax = keys[lay["K_ASPMIN"] + 1:lay["K_ASPMIN"] + 2].to(torch.int64) & 0xFFFFFFFF
+                dist.all_reduce(amin, op=dist.ReduceOp.MIN, group=group)
+                dist.all_reduce(amax, op=dist.ReduceOp.MAX, group=group)
+                keys[lay["K_ASPMIN"]] = torch.where(amin >= 2**31, amin - 2**32, amin).to(torch.int32)[0]
+                keys[lay["K_ASPMIN"] + 1] = torch.where(amax >= 2**31, amax - 2**32, amax).to(torch.int32)[0]
+                dist.all_gather_into_tensor(self.g_gcompact, self.f_gcompact, group=group)
+                dist.all_gather_into_tensor(self.g_counts, cnt[lay["C_GNC"]:lay["C_GNC"] + 1], group=group)
+            _lib.check(L.xb_nkf_range(keys.data_ptr(), f64.data_ptr(), st))
+            # 4: exact median of dh from the compact buffer(s)
+            if world > 1:
+                select(self.g_gcompact, None, world, self.gcap, self.g_counts.data_ptr(), 1, 1, cptr(lay["C_NFIN"]),
+                       cptr(lay["C_GBELOW"]), None, None, fptr(lay["F_VSHIFT"]), 1)
+            else:
+                select(self.f_gcompact, None, 1, self.gcap, cptr(lay["C_GNC"]), 1, 1, cptr(lay["C_NFIN"]),
+                       cptr(lay["C_GBELOW"]), None, None, fptr(lay["F_VSHIFT"]), 1)
+            # 5-6: sample of y per aspect bin -> per-bin brackets
+            yk(1)
+            if world > 1:
+                dist.all_gather_into_tensor(self.g_sample, self.f_sample, group=group)
+                dist.all_gather_into_tensor(self.g_sgrp, self.f_sgrp, group=group)
+                select(self.g_sample, self.g_sgrp, 1, world * self.ns, None, n_bins, 0, None, None, kptr(lay["K_BLO"]),
+                       kptr(lay["K_BLO"] + lay["MAXB"]), None, 4)
+            else:
+                select(self.f_sample, self.f_sgrp, 1, self.ns, None, n_bins, 0, None, None, kptr(lay["K_BLO"]),
+                       kptr(lay["K_BLO"] + lay["MAXB"]), None, 4)
+            # 7: the full y pass
+            yk(0)
+            if world > 1:
+                dist.all_reduce(cnt[lay["C_BTOTAL"]:lay["C_BBELOW"] + lay["MAXB"]], group=group)
+                dist.all_reduce(f64[5:8], group=group)
+                dist.all_gather_into_tensor(self.g_bkey, self.f_bkey, group=group)
+                dist.all_gather_into_tensor(self.g_bgrp, self.f_bgrp, group=group)
+                dist.all_gather_into_tensor(self.g_counts, cnt[lay["C_BNC"]:lay["C_BNC"] + 1], group=group)
+                select(self.g_bkey, self.g_bgrp, world, self.bcap, self.g_counts.data_ptr(), n_bins, 1,
+                       cptr(lay["C_BTOTAL"]), cptr(lay["C_BBELOW"]), None, None, fptr(lay["F_MED"]), 4)
+            else:
+                # 8: per-bin exact medians
+                select(self.f_bkey, self.f_bgrp, 1, self.bcap, cptr(lay["C_BNC"]), n_bins, 1, cptr(lay["C_BTOTAL"]),
+                       cptr(lay["C_BBELOW"]), None, None, fptr(lay["F_MED"]), 4)
+            _lib.check(L.xb_nkf_finalize(cnt.data_ptr(), f64.data_ptr(), self.gcap, self.bcap, st))
+            if world > 1:
+                dist.all_reduce(cnt[lay["C_FLAGS"]:lay["C_FLAGS"] + 1], op=dist.ReduceOp.MAX, group=group)
+            cnt_h = cnt.cpu().numpy()  # the iteration's only host synchronisation
+            f_h = f64.cpu().numpy()
+        return self._fast_result(cnt_h, f_h, n_bins)
+
+    def _fast_result(self, cnt_h: np.ndarray, f_h: np.ndarray, n_bins: int) -> dict[str, Any] | None:
+        lay = self.lay
+        self.fast_last_flags = int(cnt_h[lay["C_FLAGS"]])
+        if self.fast_last_flags != 0:
+            self.fast_fallbacks = getattr(self, "fast_fallbacks", 0) + 1
+            logging.info("Nuth-Kaab fast path: flags %d (1 median bracket missed, 2 compact overflow, 4 / 8 the same "
+                         "per aspect bin) -> exhaustive selection for this iteration", self.fast_last_flags)
+            return None
+        return {"n_fin": int(cnt_h[lay["C_NFIN"]]), "vshift": float(f_h[lay["F_VSHIFT"]]), "lo": float(f_h[1]),
+                "hi": float(f_h[2]), "moments": f_h[5:8].copy(),
+                "median": f_h[lay["F_MED"]:lay["F_MED"] + n_bins].copy(),
+                "counts": cnt_h[lay["C_BTOTAL"]:lay["C_BTOTAL"] + n_bins].copy()}
+
     def select_medians(self, mode: int, vshift: float, lo: float, hi: float, n_groups: int,
                        want_moments: bool = False) -> tuple[np.ndarray, np.ndarray, np.ndarray | None]:
         """Exact medians (np.nanmedian semantics: mean of the two middle values for even counts) of float32 keys by MSD
@@ -244,6 +452,13 @@ def _nuth_kaab_bin_fit_gpu(state: _NKState, vshift: float, lo: float, hi: float,
     """GPU restatement of `_nuth_kaab_bin_fit` + `_bin_or_and_fit_nd("bin_and_fit")` (affine.py:358-409,
     base.py:1006-1045): y = dh/slope_tan; p0 = (3*nanstd(y)/sqrt(2), 0, nanmean(y)); per-aspect-bin nanmedian; fit."""
     med, counts, mom = state.select_medians(1, vshift, lo, hi, int(bin_sizes), want_moments=True)
+    return _fit_from_bins(med, mom, lo, hi, bin_sizes, fit_optimizer)
+
+
+def _fit_from_bins(med: np.ndarray, mom: np.ndarray, lo: float, hi: float, bin_sizes: int,
+                   fit_optimizer: Callable[..., Any]) -> tuple[float, float, float]:
+    """Host part of `_nuth_kaab_bin_fit` (affine.py:384-409, base.py:1027-1045): p0 from the moments of y, bin mid-points,
+    the 72-point curve_fit."""
     n, s1, s2 = mom
     mean = s1 / n
     std = float(np.sqrt(max(s2 / n - mean * mean, 0.0)))
@@ -261,11 +476,27 @@ def _nuth_kaab_bin_fit_gpu(state: _NKState, vshift: float, lo: float, hi: float,
 
 
 def _nuth_kaab_iteration_step_gpu(coords_offsets: tuple[float, float, float], state: _NKState,
-                                  res: tuple[float, float], a_e: tuple[float, float], bin_sizes: int,
+                                  res_xy: tuple[float, float], a_e: tuple[float, float], bin_sizes: int,
                                   fit_optimizer: Callable[..., Any]) -> tuple[tuple[float, float, float], float]:
     """affine.py:477-536."""
     dx_px = coords_offsets[0] / a_e[0]
     dy_px = coords_offsets[1] / a_e[1]
+    if getattr(state, "use_fast", None) is None:
+        state.use_fast = state.fast_eligible(int(bin_sizes))
+    if state.use_fast:
+        res = state.iteration_fast(dx_px, dy_px, int(bin_sizes))
+        if res is not None:
+            if res["n_fin"] == 0:
+                raise ValueError(
+                    "The subsample contains no more valid values. This can happen is the horizontal shift to "
+                    "correct is very large, or if the algorithm diverged. To ensure all possible points can "
+                    "be used at any iteration step, use subsample=1."
+                )
+            vshift = res["vshift"]
+            easting, northing, _ = _fit_from_bins(res["median"], res["moments"], res["lo"], res["hi"], bin_sizes,
+                                                  fit_optimizer)
+            new_offsets = (coords_offsets[0] + easting * res_xy[0], coords_offsets[1] + northing * res_xy[1], vshift)
+            return new_offsets, float(np.sqrt(easting**2 + northing**2))
     lo, hi, n_fin = state.compute_dh(dx_px, dy_px)
     if n_fin == 0:
         raise ValueError(
@@ -276,7 +507,7 @@ def _nuth_kaab_iteration_step_gpu(coords_offsets: tuple[float, float, float], st
     med, _, _ = state.select_medians(0, 0.0, 0.0, 1.0, 1)
     vshift = float(med[0])
     easting, northing, _ = _nuth_kaab_bin_fit_gpu(state, vshift, lo, hi, bin_sizes, fit_optimizer)
-    new_offsets = (coords_offsets[0] + easting * res[0], coords_offsets[1] + northing * res[1], vshift)
+    new_offsets = (coords_offsets[0] + easting * res_xy[0], coords_offsets[1] + northing * res_xy[1], vshift)
     return new_offsets, float(np.sqrt(easting**2 + northing**2))
 
 
