@@ -65,6 +65,10 @@ int xb_set_option(const char* name, int value);
  * writes n_planes copies to dst[n_planes * n_floats] with streaming vector stores).  bench.py times it to report the
  * bandwidth that mix can reach on the box next to the roofline of the real kernel.  Not counted in xb_launch_count. */
 int xb_probe_stream(const void* src_dev, void* dst_dev, int64_t n_floats, int n_planes, void* stream);
+/* Diagnostics: the same traffic mix with the planes written by TMA bulk tensor stores (cp.async.bulk.tensor, UTMASTG) from
+ * shared-memory staged 8 x 128 tiles instead of st.global.cs -- measures whether the store instruction or the read/write
+ * mix sets the bandwidth ceiling of the terrain kernels.  dst holds n_planes planes of rows x cols float32. */
+int xb_probe_stream_tma(const void* src_dev, void* dst_dev, int64_t rows, int64_t cols, int n_planes, void* stream);
 /* Diagnostics: bit-exactness of the branch-free IEEE cores of the 3x3 windowed kernel against the CUDA round-to-nearest
  * intrinsics, over `count` consecutive float32 bit patterns x starting at bits_begin.  kind 0: the fast-path square root
  * vs __fsqrt_rn(x) (valid range [2^-101, FLT_MAX]); kind 1: the reciprocal-multiply division x / b (rcp_b = RN(1/b)) vs
@@ -139,6 +143,15 @@ int xb_bin_next(const uint32_t* key_dev, const uint16_t* bin_dev, int64_t n, int
                 uint32_t* next_key_dev, void* stream);
 int xb_bin_absdev_keys(const float* values_dev, const uint16_t* bin_dev, int64_t n, int n_bins,
                        const float* center_dev, uint32_t* key_dev, void* stream);
+
+/* Applying a 1-D binned correction -- the device side of `BiasCorr._apply_rst` for one bias variable
+ * (biascorr.py:259-310; TerrainBias: the variable is a terrain attribute): out = float32(elev + corr(var)).
+ * mode 0 "linear": `interp_nd_binning` in one dimension (spatialstats.py:237-423): piecewise-linear between the m
+ * mid-points x of the valid bins with statistics v, held constant outside.  mode 1 "per_bin": `get_perbin_nd_binning`
+ * (spatialstats.py:425-530): x = the m + 1 bin edges, v = the m statistics, the bin [left, right) holding var; NaN
+ * outside.  x_dev / v_dev are small device tables of float64. */
+int xb_bin_apply_1d(const float* elev_dev, const float* var_dev, int64_t n, const double* x_dev, const double* v_dev,
+                    int m, int mode, float* out_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Texture shading (fractional Laplacian, Brown 2010) -- the device stages of `_texture_shading_fft`

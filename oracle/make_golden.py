@@ -160,6 +160,33 @@ def binning_golden(ref) -> None:  # noqa
     print(f"binning_reference.npz: {len(store)} arrays")
 
 
+def terrainbias_golden(ref) -> None:  # noqa
+    """The "bin" branch of TerrainBias (biascorr.py:506-620) with the reference's own nd_binning, interp_nd_binning and
+    get_perbin_nd_binning (unmodified, spatialstats.py:91-530) on a synthetic pair with a curvature-dependent bias."""
+    S = ref.spatialstats
+    dem = synth.fractal_dem((200, 260), seed=7)
+    attr = ref.terrain.get_terrain_attribute(dem, "max_curvature", resolution=5.0)
+    rng = np.random.default_rng(8)
+    tba = (dem - 0.8 * np.tanh(attr / 2.0) - 0.3 + rng.normal(scale=0.05, size=dem.shape)).astype(np.float32)
+    tba[60:64, 80:100] = np.nan
+    valid = np.isfinite(dem) & np.isfinite(tba) & np.isfinite(attr)
+    diff = (dem - tba)[valid]
+    store = {"ref": dem, "tba": tba, "attr": attr.astype(np.float32)}
+    for tag, bins in (("b100", 100), ("edges", np.array([-30, -4, -2, -1, -0.5, 0, 0.5, 1, 2, 4, 30], dtype=np.float32))):
+        df = S.nd_binning(values=diff, list_var=[attr[valid]], list_var_names=["max_curvature"],
+                          list_var_bins=bins if np.isscalar(bins) else (bins,), statistics=(np.nanmedian, "count"))
+        store[f"{tag}|count"] = df["count"].values.astype(np.int64)
+        store[f"{tag}|nanmedian"] = df["nanmedian"].values.astype(np.float64)
+        store[f"{tag}|left"] = np.array([i.left for i in df["max_curvature"].values], dtype=np.float64)
+        store[f"{tag}|right"] = np.array([i.right for i in df["max_curvature"].values], dtype=np.float64)
+        fun = S.interp_nd_binning(df=df, list_var_names=["max_curvature"], statistic=np.nanmedian, min_count=0)
+        store[f"{tag}|corr_linear"] = fun((attr.flatten(),)).reshape(attr.shape).astype(np.float64)
+        store[f"{tag}|corr_perbin"] = S.get_perbin_nd_binning(df=df, list_var=[attr], list_var_names=["max_curvature"],
+                                                              statistic=np.nanmedian).astype(np.float64)
+    np.savez_compressed(os.path.join(OUT, "terrainbias_reference.npz"), **store)
+    print(f"terrainbias_reference.npz: {len(store)} arrays")
+
+
 def nk_golden(ref) -> None:  # noqa
     """Per-iteration outputs of the reference's own Nuth-Kaab code (affine.py:102-147, 477-609) on a synthetic pair."""
     import scipy.optimize
@@ -198,7 +225,10 @@ if __name__ == "__main__":
         texture_golden(load_reference())
     elif len(sys.argv) > 1 and sys.argv[1] == "binning":
         binning_golden(load_reference())
+    elif len(sys.argv) > 1 and sys.argv[1] == "terrainbias":
+        terrainbias_golden(load_reference())
     else:
         main()
         texture_golden(load_reference())
         binning_golden(load_reference())
+        terrainbias_golden(load_reference())

@@ -502,6 +502,31 @@ def test_window3_sliding_equals_generic(xb, res: float, tm: str) -> None:
         assert torch.equal(fast.view(torch.int32), ref.view(torch.int32)), (attrs, res, tm)
 
 
+@pytest.mark.parametrize("shape", [(61, 132), (777, 1028), (123, 64)])
+def test_florinsky_tma_store_variant_equals_default(xb, shape) -> None:
+    """The TMA-bulk-store variant of the packed Florinsky kernel (option ``florinsky_tma_store``, kept for A/B: measured
+    12 % slower than st.global.cs, profiles/ab_tstore_r02.txt) writes the same bits, including the NaN rim, ragged
+    tiles clipped by the tensor maps and row-sliced (shard-like) requests."""
+    import torch
+
+    from xdem_b200 import _engine, _lib
+
+    H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(9)
+    z = (1000 + torch.cumsum(torch.randn((H, W), generator=g, device="cuda"), 1)).float()
+    z[H // 2, W // 3] = float("nan")
+    for attrs in (["slope", "aspect", "hillshade", "curvature"], ["slope", "aspect", "curvature"]):
+        for rb, re in ((0, H), (7, H - 9)):
+            kw = dict(surface_fit="Florinsky", degrees=True, clip_hillshade=True, row_begin=rb, row_end=re)
+            ref = _engine.terrain_fused(z, 5.0, attrs, [], **kw)
+            _lib.set_option("florinsky_tma_store", 1)
+            try:
+                got = _engine.terrain_fused(z, 5.0, attrs, [], **kw)
+            finally:
+                _lib.set_option("florinsky_tma_store", 0)
+            assert torch.equal(got.view(torch.int32), ref.view(torch.int32)), (attrs, rb, re)
+
+
 def test_all13_split_equals_separate(xb, G) -> None:
     """BASELINE config 4's request (9 surface attributes + 4 windowed indexes, Florinsky) runs as two specialised
     launches; the planes must equal the ones of separate requests bit for bit."""

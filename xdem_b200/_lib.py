@@ -121,6 +121,10 @@ def lib() -> ctypes.CDLL:
     L.xb_bin_next.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]
     L.xb_bin_absdev_keys.restype = c_int
     L.xb_bin_absdev_keys.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]
+    L.xb_bin_apply_1d.restype = c_int
+    L.xb_bin_apply_1d.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
+    L.xb_probe_stream_tma.restype = c_int
+    L.xb_probe_stream_tma.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]
     L.xb_probe_stream.restype = c_int
     L.xb_probe_stream.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p]
     L.xb_probe_exact_math.restype = c_int
@@ -150,6 +154,6 @@ EXPORTED = ["xb_last_error", "xb_version", "xb_launch_count", "xb_terrain_fused"
             "xb_windowed_generic", "xb_set_option", "xb_shift_resample", "xb_texture_prepare", "xb_texture_filter",
             "xb_texture_finish", "xb_bin_keys", "xb_bin_hist", "xb_bin_next", "xb_bin_absdev_keys", "xb_probe_stream", "xb_probe_exact_math",
             "xb_terrain_fused_host_rows", "xb_release_scratch", "xb_variogram_pairs_xy",
-            "xb_nkf_layout", "xb_nkf_reset", "xb_nkf_dh", "xb_nkf_range", "xb_nkf_y", "xb_nkf_select", "xb_nkf_finalize", "xb_nkf_iteration"]
+            "xb_nkf_layout", "xb_nkf_reset", "xb_nkf_dh", "xb_nkf_range", "xb_nkf_y", "xb_nkf_select", "xb_nkf_finalize", "xb_nkf_iteration", "xb_bin_apply_1d", "xb_probe_stream_tma"]
 
 __all__ = ["lib", "check", "launch_count", "set_option", "XdemB200Error", "LIB_PATH", "EXPORTED"]

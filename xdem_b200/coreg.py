@@ -713,3 +713,6 @@ class NuthKaab:
     def to_translations(self) -> tuple[float, float, float]:
         o = self._meta["outputs"]["affine"]
         return o["shift_x"], o["shift_y"], o["shift_z"]
+
+
+from .biascorr import TerrainBias  # noqa: E402,F401  (xdem.coreg.TerrainBias lives next to NuthKaab)

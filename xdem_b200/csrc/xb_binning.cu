@@ -145,6 +145,55 @@ static int grid_1d(long long n, int threads, int per_sm) {
     return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Applying a 1-D binned correction (BiasCorr._apply_rst, biascorr.py:259-310): out = elev + corr(var).
+//   mode 0 "linear": interp_nd_binning (spatialstats.py:237-423) in one dimension = RegularGridInterpolator(linear) over
+//     the mid-points of the valid bins, extended by one duplicated point on each side so that values outside are held
+//     constant: corr = v[i] (1 - t) + v[i+1] t between mids i and i+1, v[0] below the first, v[m-1] above the last.
+//   mode 1 "per_bin": get_perbin_nd_binning (spatialstats.py:425-530): the statistic of the bin [left, right) that holds
+//     var, NaN outside every bin (x = the m + 1 edges, v = the m statistics).
+// float64 arithmetic like the reference, result cast to float32 (base.py:491).  HBM-bound: 12 B per pixel.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bin_apply_1d_kernel(const float* __restrict__ elev, const float* __restrict__ var, long long n,
+                    const double* __restrict__ x, const double* __restrict__ v, int m, int mode, float* __restrict__ out) {
+    extern __shared__ double sh_tab[];
+    double* sx = sh_tab;
+    double* sv = sh_tab + (mode == 1 ? m + 1 : m);
+    for (int k = threadIdx.x; k < (mode == 1 ? m + 1 : m); k += blockDim.x) sx[k] = x[k];
+    for (int k = threadIdx.x; k < m; k += blockDim.x) sv[k] = v[k];
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double a = (double)var[i];
+        double corr = CUDART_NAN;
+        if (a == a) {
+            if (mode == 0) {
+                if (a <= sx[0]) {
+                    corr = sv[0];
+                } else if (a >= sx[m - 1]) {
+                    corr = sv[m - 1];
+                } else {
+                    int lo = 0, hi = m - 1;  // sx[lo] <= a < sx[hi]
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (a >= sx[mid]) lo = mid; else hi = mid;
+                    }
+                    const double t = (a - sx[lo]) / (sx[hi] - sx[lo]);
+                    corr = sv[lo] * (1.0 - t) + sv[hi] * t;
+                }
+            } else if (a >= sx[0] && a < sx[m]) {
+                int lo = 0, hi = m;  // sx[lo] <= a < sx[hi]
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (a >= sx[mid]) lo = mid; else hi = mid;
+                }
+                corr = sv[lo];
+            }
+        }
+        out[i] = (float)((double)elev[i] + corr);
+    }
+}
+
 }  // namespace xbb
 
 extern "C" {
@@ -233,6 +282,24 @@ int xb_bin_absdev_keys(const float* values_dev, const uint16_t* bin_dev, int64_t
     }
     xbb::bin_absdev_kernel<<<xbb::grid_1d(n, xbb::NT, 16), xbb::NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         values_dev, bin_dev, n, n_bins, center_dev, key_dev);
+    XB_CUDA_CHECK(cudaGetLastError());
+    xb_count_launch(1);
+    return XB_OK;
+}
+
+int xb_bin_apply_1d(const float* elev_dev, const float* var_dev, int64_t n, const double* x_dev, const double* v_dev,
+                    int m, int mode, float* out_dev, void* stream) {
+    if (!elev_dev || !var_dev || !x_dev || !v_dev || !out_dev || n <= 0 || m < 1 || m > 4000 || (mode != 0 && mode != 1)) {
+        xb_set_error("bad arguments to xb_bin_apply_1d (1 <= m <= 4000 table entries, mode 0 linear / 1 per_bin)");
+        return XB_ERR_INVALID;
+    }
+    int sms = 0;
+    int rc = xb_num_sms(&sms);
+    if (rc) return rc;
+    const long long need = (n + 255) / 256;
+    const int grid = (int)(need < (long long)sms * 8 ? need : (long long)sms * 8);
+    xbb::bin_apply_1d_kernel<<<grid, 256, (size_t)(2 * m + 1) * sizeof(double), reinterpret_cast<cudaStream_t>(stream)>>>(
+        elev_dev, var_dev, n, x_dev, v_dev, m, mode, out_dev);
     XB_CUDA_CHECK(cudaGetLastError());
     xb_count_launch(1);
     return XB_OK;

@@ -25,6 +25,8 @@ static std::atomic<int> g_opt_fl_generic{0};
 bool xb_option_florinsky_generic() { return g_opt_fl_generic.load() != 0; }
 static std::atomic<int> g_opt_fl_packed{1};
 bool xb_option_florinsky_packed() { return g_opt_fl_packed.load() != 0; }
+static std::atomic<int> g_opt_fl_tstore{0};
+bool xb_option_florinsky_tma_store() { return g_opt_fl_tstore.load() != 0; }
 static std::atomic<int> g_opt_w3_generic{0};
 bool xb_option_window3_generic() { return g_opt_w3_generic.load() != 0; }
 static std::atomic<int> g_opt_vg_full{7};
@@ -195,6 +197,10 @@ int xb_set_option(const char* name, int value) {
     }
     if (name && strcmp(name, "florinsky_packed") == 0) {
         g_opt_fl_packed.store(value);
+        return XB_OK;
+    }
+    if (name && strcmp(name, "florinsky_tma_store") == 0) {
+        g_opt_fl_tstore.store(value);
         return XB_OK;
     }
     if (name && strcmp(name, "window3_generic") == 0) {

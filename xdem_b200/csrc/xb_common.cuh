@@ -89,5 +89,6 @@ xb_cuTensorMapEncodeTiled_t xb_get_tensormap_encoder();
 int xb_num_sms(int* out);
 bool xb_option_florinsky_generic();
 bool xb_option_florinsky_packed();   // f32x2 (FFMA2) arithmetic in the sliding Florinsky kernel
+bool xb_option_florinsky_tma_store();  // headline Florinsky requests: planes written by TMA bulk stores (A/B)
 bool xb_option_window3_generic();    // 3x3 windowed indexes through the generic fused kernel (A/B tests)
 int xb_option_variogram_full_tiles();  // bit k-1: interior tiles spanning k lag classes take the threshold-light sweep

@@ -190,11 +190,25 @@ __device__ __forceinline__ f2 atan_unit2(f2 t) {
     return fma2(mul2(t, z), q, t);
 }
 
-template <unsigned CMASK, bool FAST>
+constexpr int FL_TS_ROWS = 5;                 // TMA-store variant: rows staged per bulk store (one trip of the row ring)
+constexpr int FL_TS_PLANE = FL_TS_ROWS * 64;  // floats per plane in a warp's staging area (64-pixel-wide strip)
+
+// TST: the planes of this row go to the warp's shared-memory staging area (row-major [plane][row][64]; `stg` already
+// points at this row and lane) for a later TMA bulk store instead of to global memory.
+template <unsigned CMASK, bool FAST, bool TST = false>
 __device__ __forceinline__ void emit_row(const RowFeat2& r0, const RowFeat2& r1, const RowFeat2& r2, const RowFeat2& r3,
                                          const RowFeat2& r4, const TerrainParams& p, long long off, bool full,
-                                         int nvalid) {
+                                         int nvalid, float* stg = nullptr) {
     static_assert(CMASK != 0, "packed path: compile-time attribute mask");
+    auto put = [&](auto kc, float a, float b) {
+        constexpr int k = decltype(kc)::value;
+        if constexpr (TST) {
+            constexpr int ord = __builtin_popcount(CMASK & ((1u << k) - 1u));
+            *reinterpret_cast<float2*>(stg + ord * FL_TS_PLANE) = make_float2(a, b);
+        } else {
+            store2<FAST>(p.out[k], off, full, nvalid, a, b);
+        }
+    };
     constexpr bool NEED2 = (CMASK & ~7u) != 0;    // any second-derivative attribute
     constexpr bool NEEDALG = (CMASK & ~15u) != 0;  // curvature algebra (per-pixel FP64 numerators, curv_alg<float>)
     // z_x (fl_p, divider 420 res): 35 (D2 + 8 E2) + sum_r a_r (D_r - D2) + b_r (E_r - E2) -- the large, mutually
@@ -241,7 +255,7 @@ __device__ __forceinline__ void emit_row(const RowFeat2& r0, const RowFeat2& r1,
             const f2 a = atan_unit2(t);
             const f2 v = make_float2(b0 ? xbm::HALF_PI_F - a.x : a.x, b1 ? xbm::HALF_PI_F - a.y : a.y);
             const f2 o = fma2(v, S2(ang), car);
-            store2<FAST>(p.out[0], off, full, nvalid, o.x, o.y);
+            put(std::integral_constant<int, 0>{}, o.x, o.y);
         }
         if (CMASK & 2u) {
             const float ax0 = fabsf(zx.x), ay0 = fabsf(zy.x), ax1 = fabsf(zx.y), ay1 = fabsf(zy.y);
@@ -257,7 +271,7 @@ __device__ __forceinline__ void emit_row(const RowFeat2& r0, const RowFeat2& r1,
             v0 = zx.x < 0.0f ? xbm::TWO_PI_F - v0 : v0;
             v1 = zx.y < 0.0f ? xbm::TWO_PI_F - v1 : v1;
             const f2 o = fma2(make_float2(v0, v1), S2(ang), car);
-            store2<FAST>(p.out[1], off, full, nvalid, o.x, o.y);
+            put(std::integral_constant<int, 1>{}, o.x, o.y);
         }
         if (CMASK & 4u) {
             const float ky = p.f.hs_ky, kx = p.f.hs_nkx, sa = p.f.hs_sa, zf2 = p.f.zf2;
@@ -268,7 +282,7 @@ __device__ __forceinline__ void emit_row(const RowFeat2& r0, const RowFeat2& r1,
             const f2 h = fma2(mul2(S2(254.0f), r), inner, S2(1.5f));
             const f2 hc = make_float2(fminf(fmaxf(h.x, lo), hi), fminf(fmaxf(h.y, lo), hi));
             const f2 o = add2(hc, car);
-            store2<FAST>(p.out[2], off, full, nvalid, o.x, o.y);
+            put(std::integral_constant<int, 2>{}, o.x, o.y);
         }
     }
     if constexpr (NEED2) {
@@ -281,7 +295,7 @@ __device__ __forceinline__ void emit_row(const RowFeat2& r0, const RowFeat2& r1,
         if (CMASK & 8u) {
             const float nf = p.f.curv_nf;  // curvature = -200 (z_xx + z_yy) / d2 = (nsxx + nsyy) 200 / d2
             const f2 o = fma2(add2(nsxx, nsyy), S2(nf), car);
-            store2<FAST>(p.out[3], off, full, nvalid, o.x, o.y);
+            put(std::integral_constant<int, 3>{}, o.x, o.y);
         }
         if constexpr (NEEDALG) {
             // -z_xy sums (fl_s, 100 res^2): M11 + 2 (M12 + M21) + 4 M22, mixed second differences of D / E
@@ -290,10 +304,11 @@ __device__ __forceinline__ void emit_row(const RowFeat2& r0, const RowFeat2& r1,
             float r6a[6], r6b[6];
             curv_alg<float>(sx.x, sy.x, -nsxx.x, -nsyy.x, -nsxy.x, p, CMASK, r6a);
             curv_alg<float>(sx.y, sy.y, -nsxx.y, -nsyy.y, -nsxy.y, p, CMASK, r6b);
-#pragma unroll
-            for (int a = 0; a < 6; ++a)
-                if (CMASK & (1u << (4 + a)))
-                    store2<FAST>(p.out[4 + a], off, full, nvalid, r6a[a] + car.x, r6b[a] + car.y);
+#define XB_FL_PUT_ALG(A)                             \
+    if constexpr ((CMASK & (1u << (4 + A))) != 0) \
+        put(std::integral_constant<int, 4 + A>{}, r6a[A] + car.x, r6b[A] + car.y);
+            XB_FL_PUT_ALG(0) XB_FL_PUT_ALG(1) XB_FL_PUT_ALG(2) XB_FL_PUT_ALG(3) XB_FL_PUT_ALG(4) XB_FL_PUT_ALG(5)
+#undef XB_FL_PUT_ALG
         }
     }
 }
@@ -405,6 +420,115 @@ florinsky_sliding_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// TMA-store variant of the packed kernel.  The r02 streaming probes (profiles/tma_store_probe_r02*.txt) show that for the
+// terrain traffic mix (1 plane read, 3-4 written) bulk tensor stores from shared memory reach 5.5-6.0 TB/s where
+// st.global.cs vectors stop at 5.35-5.45 TB/s.  Every warp stages FL_TS_ROWS rows of its 64-pixel strip per plane in
+// shared memory and lane 0 issues one cp.async.bulk.tensor.2d store per plane; the tensor maps clip at the raster /
+// shard edges, so this variant has no edge paths at all.
+// ---------------------------------------------------------------------------------------------------------------
+struct OutMaps {
+    CUtensorMap m[4];
+};
+
+template <unsigned CMASK>
+__global__ void __launch_bounds__(NTHREADS, 2)
+florinsky_sliding_tstore_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ OutMaps omaps,
+                                const __grid_constant__ TerrainParams p) {
+    constexpr int NP = __builtin_popcount(CMASK);
+    constexpr uint32_t STAGE_BYTES = BOXW * FL_BOXH * sizeof(float);
+    constexpr int STAGE_ELEMS = ((STAGE_BYTES + 127) / 128) * 128 / sizeof(float);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* smem = reinterpret_cast<float*>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar[NSTAGES];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wx = warp & 1, wy = warp >> 1;
+    const long long tiles_x = p.tiles_x, ntiles = p.ntiles, W = p.cols;
+    float* wstage = smem + (size_t)NSTAGES * STAGE_ELEMS + (size_t)warp * (NP * FL_TS_PLANE);
+
+    if (tid == 0) {
+        xb_prefetch_tensormap(&tmap);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) xb_prefetch_tensormap(&omaps.m[k]);
+#pragma unroll
+        for (int s = 0; s < NSTAGES; ++s) xb_mbar_init(&full_bar[s], 1);
+        xb_fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGES; ++s) {
+            const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+            if (t < ntiles) {
+                const int ty = (int)(t / tiles_x), tx = (int)(t % tiles_x);
+                xb_mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                xb_tma_load_2d(smem + (size_t)s * STAGE_ELEMS, &tmap, &full_bar[s], tx * TW - XOFF,
+                               (int)p.row_begin + ty * FL_TH - 2);
+            }
+        }
+    }
+    int it = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int stage = it % NSTAGES;
+        const int ty = (int)(t / tiles_x), tx = (int)(t % tiles_x);
+        const long long y_tile = p.row_begin + (long long)ty * FL_TH;
+        const long long xs = (long long)tx * TW + wx * 64;  // first column of the warp's strip
+        float* tile = smem + (size_t)stage * STAGE_ELEMS;
+        xb_mbar_wait(&full_bar[stage], (uint32_t)((it / NSTAGES) & 1));
+        const float* base = tile + (size_t)(wy * FL_RPW) * BOXW + (XOFF + wx * 64 + 2 * lane - 2);
+        const long long y_first = y_tile + wy * FL_RPW;
+        if (xs < W && y_first < p.row_end) {
+            RowFeat2 f0, f1, f2, f3, f4;
+            make_features(base + 0 * BOXW, f0);
+            make_features(base + 1 * BOXW, f1);
+            make_features(base + 2 * BOXW, f2);
+            make_features(base + 3 * BOXW, f3);
+#pragma unroll 1
+            for (int g = 0; g < FL_RPW / 5; ++g) {
+                const float* rp = base + (size_t)(4 + 5 * g) * BOXW;
+                float* sp = wstage + 2 * lane;
+                // the previous bulk stores of this warp must have finished READING the staging area
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+#define XB_FL_STEP(NEW, A, B, C, D, E)                             \
+    make_features(rp, NEW);                                        \
+    emit_row<CMASK, true, true>(A, B, C, D, E, p, 0, true, 2, sp); \
+    rp += BOXW, sp += 64;
+                XB_FL_STEP(f4, f0, f1, f2, f3, f4)
+                XB_FL_STEP(f0, f1, f2, f3, f4, f0)
+                XB_FL_STEP(f1, f2, f3, f4, f0, f1)
+                XB_FL_STEP(f2, f3, f4, f0, f1, f2)
+                XB_FL_STEP(f3, f4, f0, f1, f2, f3)
+#undef XB_FL_STEP
+                xb_fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    const int oy = (int)(y_first - p.row_begin) + 5 * g;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k)
+                        asm volatile(
+                            "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                reinterpret_cast<uint64_t>(&omaps.m[k])),
+                            "r"(xb_smem_u32(wstage + k * FL_TS_PLANE)), "r"((int)xs), "r"(oy)
+                            : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const long long tn = t + (long long)NSTAGES * gridDim.x;
+            if (tn < ntiles) {
+                const int tyn = (int)(tn / tiles_x), txn = (int)(tn % tiles_x);
+                xb_mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                xb_tma_load_2d(tile, &tmap, &full_bar[stage], txn * TW - XOFF, (int)p.row_begin + tyn * FL_TH - 2);
+            }
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA exits
+}
+
 // Eligibility: float32, Florinsky surface attributes only, 16-byte aligned raster (TMA), no windowed indexes.
 int launch_florinsky_sliding(const TerrainParams& p_in, cudaStream_t stream) {
     TerrainParams p = p_in;
@@ -450,6 +574,43 @@ int launch_florinsky_sliding(const TerrainParams& p_in, cudaStream_t stream) {
     };
     // 2 CTAs/SM: the 5-row feature ring needs ~100 registers (a 3-CTA build spills and measured 40 % slower).
     // The two headline requests get compile-time attribute masks.
+    // TMA-store variant for the two headline requests when every plane is 16-byte aligned with a 16-byte pitch
+    if (xb_option_florinsky_packed() && xb_option_florinsky_tma_store() && (p.surf_mask == 15u || p.surf_mask == 11u)) {
+        bool ok = (p.out_ld * 4) % 16 == 0 && p.cols < (1ll << 31) && (p.row_end - p.row_begin) < (1ll << 31);
+        for (int i = 0; i < 4; ++i)
+            if (((p.surf_mask >> i) & 1u) && reinterpret_cast<uintptr_t>(p.out[i]) % 16 != 0) ok = false;
+        OutMaps om;
+        memset(&om, 0, sizeof(om));
+        int np = 0;
+        for (int i = 0; i < 4 && ok; ++i) {
+            if (!((p.surf_mask >> i) & 1u)) continue;
+            cuuint64_t od[2] = {(cuuint64_t)p.cols, (cuuint64_t)(p.row_end - p.row_begin)};
+            cuuint64_t os[1] = {(cuuint64_t)(p.out_ld * 4)};
+            cuuint32_t ob[2] = {64u, (cuuint32_t)FL_TS_ROWS};
+            cuuint32_t oe[2] = {1, 1};
+            if (enc(&om.m[np++], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p.out[i], od, os, ob, oe,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                ok = false;
+        }
+        if (ok) {
+            const size_t smem_ts = smem + (size_t)NWARPS * np * FL_TS_PLANE * sizeof(float);
+            auto launch_ts = [&](auto kern) -> int {
+                XB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts));
+                int occ = 0;
+                XB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTHREADS, smem_ts));
+                if (occ < 1) occ = 1;
+                long long grid = (long long)num_sms * occ;
+                if (grid > p.ntiles) grid = p.ntiles;
+                kern<<<(unsigned)grid, NTHREADS, smem_ts, stream>>>(tmap, om, p);
+                XB_CUDA_CHECK(cudaGetLastError());
+                xb_count_launch(1);
+                return XB_OK;
+            };
+            return p.surf_mask == 15u ? launch_ts(florinsky_sliding_tstore_kernel<15u>)
+                                      : launch_ts(florinsky_sliding_tstore_kernel<11u>);
+        }
+    }
     // Packed (f32x2) kernels with compile-time masks for the common requests: the API default DEM.slope() / aspect /
     // hillshade and their combinations (first derivatives only), the two headline requests, curvature, and the
     // "all attributes" request of BASELINE config 4 (nine planes, with and without the deprecated `curvature`).
