@@ -155,7 +155,7 @@ int xb_build_terrain_params(xbt::TerrainParams& p, int dtype, double resolution,
         // Markstein's correctly rounded a/b needs a mantissa of b that is not all ones
         uint32_t llbits;
         memcpy(&llbits, &ll, 4);
-        p.rug_fast_ok = (r >= 1e-6 && r <= 1e8 && (llbits & 0x7fffffu) != 0x7fffffu) ? 1 : 0;
+        p.rug_fast_ok = (r >= 1e-6 && r <= 1e6 && (llbits & 0x7fffffu) != 0x7fffffu) ? 1 : 0;
     } else {
         const double diag = sqrt(2.0) * r;
         p.rug_dl2_diag = diag * diag;
@@ -175,8 +175,8 @@ int xb_build_terrain_params(xbt::TerrainParams& p, int dtype, double resolution,
     p.f.rug_l2s = (float)p.rug_dl2_straight;
     p.f.rug_l2d = (float)p.rug_dl2_diag;
     p.f.one = 1.0f;
-    p.f.rug_y4 = -0.25f * p.f.rug_rcp_ll;
-    p.f.rug_b4 = -4.0f * p.f.rug_nll;
+    p.f.rug_y4 = -0.0625f * p.f.rug_rcp_ll;
+    p.f.rug_b4 = -16.0f * p.f.rug_nll;
     *hs_out = hs;
     *hw_out = hw;
     return XB_OK;

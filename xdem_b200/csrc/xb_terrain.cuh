@@ -36,7 +36,7 @@ struct TerrainParams {
     struct F32 {
         float inv1, ang, hs_ky, hs_nkx, hs_sa, zf2, curv_nf, alg_c2, rug_rcp_ll, rug_nll, rug_l2s, rug_l2d;
         float one;  // 1.0f as a run-time value (addp2, xb_terrain_dev.cuh)
-        float rug_y4, rug_b4;  // -RN(1/L^2)/4 and +4 L^2: division of the negated, x4-scaled area sum (xb_terrain_w3.cu)
+        float rug_y4, rug_b4;  // -RN(1/L^2)/16 and +16 L^2: division of the negated, x16-scaled area sum (xb_terrain_w3.cu)
     } f;
     int rug_fast_ok;       // resolution inside the argument range of the fast IEEE sqrt / division (xb_terrain_w3.cu)
 };
