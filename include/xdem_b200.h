@@ -255,6 +255,17 @@ int xb_nk_aux(const float* ref_dev, int64_t rows_buf, int64_t cols, int64_t ld, 
               int bottom_is_border, int64_t row_begin, int64_t row_end, float* slope_tan_dev, float* aspect_dev,
               int64_t out_ld, void* stream);
 
+/* xb_nk_aux fused with the validity mask of the fit (`_preprocess_rst_pts_subsample`, base.py:653-661):
+ * sub_mask = inlier (NULL: all) & finite(ref, tba, slope_tan, aspect), n_valid_dev[0] = its population, and
+ * range_cand_dev (uint32[4 + 2*64]) = {aspect min bits, max bits over the valid pixels, n_min, n_max, up to 64 pixel
+ * indices attaining the minimum, up to 64 attaining the maximum} -- what xb_nkf_iteration needs to confirm the aspect
+ * range of an iteration without re-reading the aspect plane.  tba_dev points at the to-be-aligned row of output row 0;
+ * slope_tan / aspect / sub_mask are contiguous (row_end - row_begin) x cols. */
+int xb_nk_prepare(const float* ref_dev, int64_t rows_buf, int64_t cols, int64_t ld, int top_is_border,
+                  int bottom_is_border, int64_t row_begin, int64_t row_end, const float* tba_dev, int64_t tba_ld,
+                  const uint8_t* inlier_dev, float* slope_tan_dev, float* aspect_dev, uint8_t* sub_mask_dev,
+                  unsigned long long* n_valid_dev, uint32_t* range_cand_dev, void* stream);
+
 /* dh = ref - bilinear(tba at (row + dy_px, col + dx_px)) where sub_mask != 0, NaN elsewhere (affine.py:179-184;
  * geoutils `_interp_points`, linear, NaN-propagating -- restated).  dh / sub_mask / aspect are
  * contiguous rows x cols; tba_dev is a buffer of tba_rows_total rows whose row `tba_row0` is raster row 0 of this
@@ -329,7 +340,8 @@ int xb_nkf_dh(int sample, const float* ref_dev, const float* tba_dev, const uint
 /* f64[aspect range] = float32 min / max of the aspect over finite dh (after the counters were all-reduced) */
 int xb_nkf_range(const uint32_t* keys_dev, double* f64_dev, void* stream);
 /* sample != 0: (key of y, aspect bin) of the sampled rows -> skey_dev / sgrp_dev.  sample == 0: every pixel -> per-bin
- * totals / below-bracket counts / moments into cnt / f64, in-bracket (key, bin) pairs appended to bkey_dev / bgrp_dev. */
+ * above-bracket (cnt[C_BTOTAL..]) / below-bracket counts / moments into cnt / f64, in-bracket (key, bin) pairs appended
+ * to bkey_dev / bgrp_dev; xb_nkf_select mode 2 turns the above-counts into the bin totals. */
 int xb_nkf_y(int sample, const float* dh_dev, const float* slope_tan_dev, const float* aspect_dev, uint8_t* bin_cache_dev,
              int64_t rows, int64_t cols, int n_bins, uint32_t* skey_dev, uint8_t* sgrp_dev, int stride, uint32_t seed,
              unsigned long long* cnt_dev, const uint32_t* keys_dev, double* f64_dev, uint32_t* bkey_dev,
@@ -337,23 +349,28 @@ int xb_nkf_y(int sample, const float* dh_dev, const float* slope_tan_dev, const 
 /* Two order statistics per group of a small key buffer by 4 x (digit histogram + device-side digit pick).  mode 0: the
  * bracket keys around the sample median of each group -> out_lo_dev / out_hi_dev; mode 1: the exact median of the
  * population (ext_total elements, ext_below below the bracket) from the compact buffer -> out_val_dev (mean of the two
- * middle float32 values in float64, NaN for an empty group); a rank outside the buffer sets miss_bit in flags_dev[0]. */
+ * middle float32 values in float64, NaN for an empty group); a rank outside the buffer sets miss_bit in flags_dev[0].
+ * mode 2: like 1, but ext_total_dev arrives holding the count ABOVE the bracket (what xb_nkf_y accumulates): the
+ * population is above + below + the group's entries in the buffer, and that total is written back to ext_total_dev. */
 int xb_nkf_select(const uint32_t* key_dev, const uint8_t* grp_dev, int64_t n_seg, int64_t seg_cap,
                   const unsigned long long* seg_count_dev, int64_t seg_count_stride, int n_groups, int mode,
-                  const unsigned long long* ext_total_dev, const unsigned long long* ext_below_dev, uint32_t* out_lo_dev,
+                  unsigned long long* ext_total_dev, const unsigned long long* ext_below_dev, uint32_t* out_lo_dev,
                   uint32_t* out_hi_dev, double* out_val_dev, unsigned long long* flags_dev, uint64_t miss_bit,
                   uint32_t* hist_dev, uint32_t* prefix_dev, unsigned long long* below_dev, long long* rank_dev,
                   void* stream);
 int xb_nkf_finalize(unsigned long long* cnt_dev, double* f64_dev, uint64_t gcap, uint64_t bcap, void* stream);
 /* One whole single-GPU iteration: the calls above in order (sample_dev / sgrp_dev hold ns = 4 * ceil(rows*cols/4/stride)
- * entries and are reused for the dh and the y sample). */
+ * entries and are reused for the dh and the y sample).  range_cand_dev (from xb_nk_prepare, or NULL): with it the dh pass
+ * does not read the aspect plane -- the aspect range is confirmed on the candidates, with a full reduction only when
+ * every candidate lost its dh.  aspect_dev may be NULL in xb_nkf_dh(sample = 0) for the same purpose. */
 int xb_nkf_iteration(const float* ref_dev, const float* tba_dev, const uint8_t* sub_mask_dev, const float* slope_tan_dev,
                      const float* aspect_dev, int64_t rows, int64_t cols, int64_t ld, int64_t tba_ld, int64_t tba_row0,
                      int64_t tba_rows_total, double dx_px, double dy_px, int n_bins, float* dh_dev, uint8_t* bin_cache_dev,
                      uint32_t* sample_dev, uint8_t* sgrp_dev, int64_t ns, int stride, uint32_t seed,
                      uint32_t* gcompact_dev, uint64_t gcap, uint32_t* bkey_dev, uint8_t* bgrp_dev, uint64_t bcap,
                      unsigned long long* cnt_dev, uint32_t* keys_dev, double* f64_dev, uint32_t* hist_dev,
-                     uint32_t* prefix_dev, unsigned long long* below_dev, long long* rank_dev, void* stream);
+                     uint32_t* prefix_dev, unsigned long long* below_dev, long long* rank_dev,
+                     const uint32_t* range_cand_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,6 @@
 #!/bin/bash
-# per-kernel device times of one bracketed-selection Nuth-Kaab iteration at 16384^2 (third iteration of nk_fast_prof.py)
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"nkf_|sel_" -s 78 -c 39 --csv --log-file gpurun_out/nkf_launches.csv python scripts/nk_fast_prof.py > /dev/null 2>&1
+# per-kernel device times of one Nuth-Kaab fit at 16384^2 (second fit of nk_breakdown.py: preparation + iterations)
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"nk_|nkf_|sel_" -s 372 -c 76 --csv --log-file gpurun_out/nkf_launches.csv python scripts/nk_breakdown.py > /dev/null 2>&1
 python - <<"PY"
 import csv
 rows = list(csv.reader(open("gpurun_out/nkf_launches.csv")))
@@ -13,15 +13,9 @@ for r in rows:
     key = (d["ID"], d["Kernel Name"][:40])
     agg.setdefault(key, {})[d["Metric Name"]] = (d["Metric Value"], d["Metric Unit"])
     if key not in order: order.append(key)
-tot = 0; by = {}
 for k in order:
     m = agg[k]
     t = float(m["gpu__time_duration.sum"][0].replace(",", "")); u = m["gpu__time_duration.sum"][1]
     t_us = t / 1000 if u in ("ns", "nsecond") else t
-    tot += t_us
-    name = k[1].split("(")[0]
-    by.setdefault(name, [0, 0.0]); by[name][0] += 1; by[name][1] += t_us
-    if t_us > 100: print(k[0], k[1], f"{t_us:9.1f} us", m.get("dram__bytes_read.sum"), m.get("dram__bytes_write.sum"))
-for n, (c, t) in by.items(): print(f"{n:45s} x{c:3d} {t:9.1f} us")
-print("total us", tot)
+    print(k[0], k[1], f"{t_us:9.1f} us", m.get("dram__bytes_read.sum"), m.get("dram__bytes_write.sum"))
 PY

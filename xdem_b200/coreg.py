@@ -12,6 +12,7 @@ loop and stopping rule (affine.py:102-147).
 from __future__ import annotations
 
 import ctypes
+import os
 import logging
 from typing import Any, Callable, Iterable
 
@@ -23,6 +24,7 @@ from . import _arrays, _lib
 
 #: bracketed exact selection (csrc/xb_nk_fast.cu) for rasters of >= 2^20 pixels; False forces the exhaustive radix select
 NK_FAST = True
+NK_SAMPLE = int(os.environ.get("XDEM_B200_NK_SAMPLE", 4_000_000))  # sampled pixels for the selection brackets
 
 
 def _nuth_kaab_fit_func(xx: np.ndarray, *params: float) -> np.ndarray:
@@ -72,29 +74,59 @@ class _NKState:
         n = self.rows * self.cols
         rtop, rbot = ref_halo if ref_halo is not None else (None, None)
         ttop, tbot = tba_halo if tba_halo is not None else (None, None)
-        ref_buf = torch.cat([t for t in (rtop, ref, rbot) if t is not None]).contiguous()
+        parts = [t for t in (rtop, ref, rbot) if t is not None]
+        ref_buf = (torch.cat(parts) if len(parts) > 1 else ref).contiguous()  # no copy without halos
         self._ref_buf = ref_buf
         r0 = 0 if rtop is None else rtop.shape[0]
         self.ref = ref_buf[r0:r0 + self.rows]
-        self.tba_buf = torch.cat([t for t in (ttop, tba, tbot) if t is not None]).contiguous()
+        parts = [t for t in (ttop, tba, tbot) if t is not None]
+        self.tba_buf = (torch.cat(parts) if len(parts) > 1 else tba).contiguous()
         self.tba_row0 = 0 if ttop is None else ttop.shape[0]
         self.tba_halo_rows = (self.tba_row0, 0 if tbot is None else tbot.shape[0])
         self.tba = self.tba_buf[self.tba_row0:self.tba_row0 + self.rows]
         self.slope_tan = torch.empty((self.rows, self.cols), dtype=torch.float32, device=self.dev)
         self.aspect = torch.empty_like(self.slope_tan)
-        with torch.cuda.device(self.dev):
-            _lib.check(self.L.xb_nk_aux(ref_buf.data_ptr(), ref_buf.shape[0], self.cols, ref_buf.stride(0),
-                                        int(rtop is None), int(rbot is None), r0, r0 + self.rows,
-                                        self.slope_tan.data_ptr(), self.aspect.data_ptr(), self.cols, self.stream))
-        # valid mask: inlier & finite(ref, tba, slope_tan, aspect)  (base.py:653-661)
-        valid = torch.isfinite(self.ref) & torch.isfinite(self.tba) & torch.isfinite(self.slope_tan) \
-            & torch.isfinite(self.aspect)
+        # one pass: aux variables + valid mask = inlier & finite(ref, tba, slope_tan, aspect) (base.py:653-661) + its
+        # count + the static aspect range with the pixels that attain it (xb_nk_prepare)
+        inl = None
         if inlier_mask is not None:
-            valid &= inlier_mask.to(self.dev).bool()
-        self.valid = valid
-        self.sub_mask = valid.to(torch.uint8).contiguous()
+            inl = inlier_mask.to(self.dev)
+            inl = (inl if inl.dtype in (torch.bool, torch.uint8) else inl != 0).contiguous()
+            if inl.shape != ref.shape:
+                raise ValueError("inlier_mask must have the shape of the rasters")
+            if inl.dtype == torch.bool:
+                inl = inl.view(torch.uint8)
+        self.sub_mask = torch.empty((self.rows, self.cols), dtype=torch.uint8, device=self.dev)
+        self._n_valid_t = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.range_cand = torch.zeros(4 + 2 * 64, dtype=torch.int32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(self.L.xb_nk_prepare(ref_buf.data_ptr(), ref_buf.shape[0], self.cols, ref_buf.stride(0),
+                                            int(rtop is None), int(rbot is None), r0, r0 + self.rows,
+                                            self.tba.data_ptr(), self.tba_buf.stride(0),
+                                            inl.data_ptr() if inl is not None else None, self.slope_tan.data_ptr(),
+                                            self.aspect.data_ptr(), self.sub_mask.data_ptr(),
+                                            self._n_valid_t.data_ptr(), self.range_cand.data_ptr(), self.stream))
+        self._inl_keepalive = inl
+        self._valid = None
         self.dh = torch.empty(n, dtype=torch.float32, device=self.dev)
         self.n = n
+
+    @property
+    def valid(self) -> torch.Tensor:
+        """Boolean valid mask of the fit (before any subsampling), materialised on demand."""
+        if self._valid is None:
+            self._valid = self.sub_mask.bool()
+        return self._valid
+
+    def n_valid(self) -> int:
+        return int(self._n_valid_t.item())
+
+    def set_subsample(self, mask_u8: torch.Tensor) -> None:
+        """Restrict the fit to a subset of the valid pixels.  The static aspect range of xb_nk_prepare belongs to the
+        full valid set, so the per-iteration range falls back to the reduction inside the dh pass."""
+        _ = self.valid  # cache the full mask before sub_mask is replaced
+        self.sub_mask = mask_u8
+        self.range_cand = None
 
     # ------------------------------------------------------------------ device passes
     def compute_dh(self, dx_px: float, dy_px: float) -> tuple[float, float, int]:
@@ -178,8 +210,8 @@ class _NKState:
         world = dist.get_world_size(self.group) if (self.sharded and dist.is_initialized()) else 1
         self._world = world
         n_global = self._n_global
-        # ~8 M sampled pixels over the whole raster: one 4-pixel chunk out of every `stride`, jittered
-        self.stride = max(1, int(n_global // 8_000_000))
+        # ~4 M sampled pixels over the whole raster (measured optimum of sample cost vs bracket width at 16384^2): one 4-pixel chunk out of every `stride`, jittered
+        self.stride = max(1, int(n_global // NK_SAMPLE))
         n_schunks = (self.rows * (self.cols // 4) + self.stride - 1) // self.stride
         ns = 4 * n_schunks
         if world > 1:
@@ -277,7 +309,8 @@ class _NKState:
                     self.f_bins.data_ptr(), self.f_sample.data_ptr(), self.f_sgrp.data_ptr(), self.ns, self.stride, seed,
                     self.f_gcompact.data_ptr(), self.gcap, self.f_bkey.data_ptr(), self.f_bgrp.data_ptr(), self.bcap,
                     cnt.data_ptr(), keys.data_ptr(), f64.data_ptr(), self.f_hist.data_ptr(), self.f_prefix.data_ptr(),
-                    self.f_below.data_ptr(), self.f_rank.data_ptr(), st))
+                    self.f_below.data_ptr(), self.f_rank.data_ptr(),
+                    self.range_cand.data_ptr() if self.range_cand is not None else None, st))
                 cnt_h = cnt.cpu().numpy()  # the iteration's only host synchronisation
                 f_h = f64.cpu().numpy()
             return self._fast_result(cnt_h, f_h, n_bins)
@@ -330,11 +363,11 @@ class _NKState:
                 dist.all_gather_into_tensor(self.g_bkey, self.f_bkey, group=group)
                 dist.all_gather_into_tensor(self.g_bgrp, self.f_bgrp, group=group)
                 dist.all_gather_into_tensor(self.g_counts, cnt[lay["C_BNC"]:lay["C_BNC"] + 1], group=group)
-                select(self.g_bkey, self.g_bgrp, world, self.bcap, self.g_counts.data_ptr(), n_bins, 1,
+                select(self.g_bkey, self.g_bgrp, world, self.bcap, self.g_counts.data_ptr(), n_bins, 2,
                        cptr(lay["C_BTOTAL"]), cptr(lay["C_BBELOW"]), None, None, fptr(lay["F_MED"]), 4)
             else:
                 # 8: per-bin exact medians
-                select(self.f_bkey, self.f_bgrp, 1, self.bcap, cptr(lay["C_BNC"]), n_bins, 1, cptr(lay["C_BTOTAL"]),
+                select(self.f_bkey, self.f_bgrp, 1, self.bcap, cptr(lay["C_BNC"]), n_bins, 2, cptr(lay["C_BTOTAL"]),
                        cptr(lay["C_BBELOW"]), None, None, fptr(lay["F_MED"]), 4)
             _lib.check(L.xb_nkf_finalize(cnt.data_ptr(), f64.data_ptr(), self.gcap, self.bcap, st))
             if world > 1:
@@ -548,7 +581,7 @@ def nuth_kaab(ref_elev: Any, tba_elev: Any, inlier_mask: Any = None, transform: 
     if inlier_mask is not None:
         mask_t = inlier_mask if isinstance(inlier_mask, torch.Tensor) else torch.from_numpy(np.asarray(inlier_mask))
     state = _NKState(ref_t, tba_t, mask_t)
-    n_valid = int(state.valid.sum().item())
+    n_valid = state.n_valid()
     if n_valid == 0:
         raise ValueError(
             "There is no valid points common to the input and auxiliary data (bias variables, or "
@@ -564,7 +597,7 @@ def nuth_kaab(ref_elev: Any, tba_elev: Any, inlier_mask: Any = None, transform: 
             pick = torch.from_numpy(rng.choice(n_valid, size=want, replace=False)).to(state.dev)
             m = torch.zeros(state.n, dtype=torch.uint8, device=state.dev)
             m[idx_valid[pick]] = 1
-            state.sub_mask = m.view(state.rows, state.cols).contiguous()
+            state.set_subsample(m.view(state.rows, state.cols).contiguous())
             n_valid = want
     offsets = _iterate_nuth_kaab(state, transform, int(pf["bin_sizes"]), pf["fit_optimizer"], tolerance,
                                  max_iterations)

@@ -28,6 +28,8 @@
 
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "xb_common.cuh"
 
 namespace xbf {
@@ -36,7 +38,7 @@ constexpr int NT = 256;
 constexpr int MAXB = 96;
 constexpr int WSTAGE = 640;  // per-warp staging of compacted entries (a warp sees 2048 pixels of a 16384-wide row)
 // layout of the small device state arrays (also exported through xb_nkf_layout)
-enum { C_NFIN = 0, C_GBELOW = 1, C_GNC = 2, C_BNC = 3, C_FLAGS = 4, C_BTOTAL = 8, C_BBELOW = 8 + MAXB, C_SIZE = 8 + 2 * MAXB };
+enum { C_NFIN = 0, C_GBELOW = 1, C_GNC = 2, C_BNC = 3, C_FLAGS = 4, C_RFALL = 5, C_BTOTAL = 8, C_BBELOW = 8 + MAXB, C_SIZE = 8 + 2 * MAXB };
 enum { K_ASPMIN = 0, K_ASPMAX = 1, K_GLO = 2, K_GHI = 3, K_BLO = 4, K_BHI = 4 + MAXB, K_SIZE = 4 + 2 * MAXB };
 enum { F_VSHIFT = 0, F_ASPLO = 1, F_ASPHI = 2, F_CLO = 3, F_CHI = 4, F_M0 = 5, F_MED = 8, F_SIZE = 8 + MAXB };
 enum { FLAG_GMISS = 1, FLAG_GOVER = 2, FLAG_BMISS = 4, FLAG_BOVER = 8 };
@@ -151,8 +153,10 @@ nkf_dh_kernel(const DhArgs a, float* __restrict__ dh, unsigned* __restrict__ sam
                 dh4(a.ref, a.tba, a.sub_mask, r, c, a.cols, a.ld, a.tba_ld, a.tba_row0, a.tba_rows_total, a.i0, a.j0,
                     a.w00, a.w01, a.w10, a.w11, out);
                 *reinterpret_cast<float4*>(dh + r * a.cols + c) = make_float4(out[0], out[1], out[2], out[3]);
-                const float4 a4 = *reinterpret_cast<const float4*>(a.aspect + r * a.cols + c);
-                as[0] = a4.x, as[1] = a4.y, as[2] = a4.z, as[3] = a4.w;
+                if (a.aspect) {  // NULL: the aspect range comes from nkf_range_check_kernel (single GPU)
+                    const float4 a4 = *reinterpret_cast<const float4*>(a.aspect + r * a.cols + c);
+                    as[0] = a4.x, as[1] = a4.y, as[2] = a4.z, as[3] = a4.w;
+                }
             }
             unsigned key[4];
             unsigned tmask = 0u;
@@ -213,8 +217,8 @@ nkf_dh_kernel(const DhArgs a, float* __restrict__ dh, unsigned* __restrict__ sam
         below += __shfl_xor_sync(0xffffffffu, below, o);
     }
     if (lane == 0) {
-        if (lmin != 0xffffffffu) atomicMin(&keys[K_ASPMIN], lmin);
-        if (nfin) atomicMax(&keys[K_ASPMAX], lmax);
+        if (a.aspect && lmin != 0xffffffffu) atomicMin(&keys[K_ASPMIN], lmin);
+        if (a.aspect && nfin) atomicMax(&keys[K_ASPMAX], lmax);
         if (nfin) atomicAdd(&cnt[C_NFIN], nfin);
         if (below) atomicAdd(&cnt[C_GBELOW], below);
     }
@@ -253,7 +257,6 @@ nkf_y_kernel(const float* __restrict__ dh, const float* __restrict__ slope_tan, 
              unsigned* __restrict__ skey, unsigned char* __restrict__ sgrp, int stride, unsigned seed, long long n_schunks,
              unsigned long long* __restrict__ cnt, const unsigned* __restrict__ keys, double* __restrict__ f64,
              unsigned* __restrict__ bkey, unsigned char* __restrict__ bgrp, unsigned long long bcap) {
-    __shared__ unsigned s_total[MAXB + 1], s_below[MAXB + 1], s_lo[MAXB + 1], s_hi[MAXB + 1];
     const double vshift = f64[F_VSHIFT], lo = f64[F_ASPLO], hi = f64[F_ASPHI];
     const bool reuse = !SAMPLE && f64[F_CLO] == lo && f64[F_CHI] == hi;
     const double step = (hi - lo) / (double)n_bins;
@@ -283,120 +286,140 @@ nkf_y_kernel(const float* __restrict__ dh, const float* __restrict__ slope_tan, 
         }
         return;
     }
+    // FULL pass.  Shared state, addressed through 32-bit shared-window addresses (plain LEA + LDS / ATOMS; static
+    // __shared__ arrays indexed per pixel cost a chain of uniform-datapath address instructions each time):
+    //   s_lohi[b]       bracket (lo, hi) of bin b; slot MAXB = (0xffffffff, 0): nothing is ever inside it
+    //   s_cnt[b]        keys of bin b below the bracket;  s_cnt[MAXB + 1 + b]  keys above it;  slot MAXB: sink
+    // A pixel does exactly ONE unconditional shared-memory increment -- below, above, or the sink (in-bracket pixels are
+    // counted by the selection's first histogram, invalid ones not at all) -- so the per-pixel code is branch-free.
+    // The bin totals follow in sel_pick_kernel (mode 2): N = below + above + in-bracket.
+    __shared__ uint2 s_lohi[MAXB + 1];
+    __shared__ unsigned s_cnt[2 * (MAXB + 1)];
     __shared__ unsigned s_stage[NT / 32][WSTAGE];
     __shared__ unsigned char s_stage_g[NT / 32][WSTAGE];
     const int warp = threadIdx.x >> 5;
-    unsigned wn = 0;
-    for (int k = threadIdx.x; k < n_bins; k += NT) {
-        s_total[k] = s_below[k] = 0u;
-        s_lo[k] = keys[K_BLO + k], s_hi[k] = keys[K_BHI + k];
-    }
-    if (threadIdx.x == 0) s_lo[MAXB] = 0xffffffffu, s_hi[MAXB] = 0u;
+    for (int k = threadIdx.x; k < 2 * (MAXB + 1); k += NT) s_cnt[k] = 0u;
+    for (int k = threadIdx.x; k <= MAXB; k += NT)
+        s_lohi[k] = k < n_bins ? make_uint2(keys[K_BLO + k], keys[K_BHI + k]) : make_uint2(0xffffffffu, 0u);
     __syncthreads();
+    const unsigned lohi_addr = (unsigned)__cvta_generic_to_shared(s_lohi);
+    const unsigned cnt_addr = (unsigned)__cvta_generic_to_shared(s_cnt);
     const int lane = threadIdx.x & 31;
+    // dh - vshift: the reference subtracts in float64 and rounds to float32; when the median is itself a float32 (odd
+    // count, or two equal middle values) the float32 subtraction rounds identically (the float64 difference of two
+    // floats is exact unless their exponents are > 29 apart, where both forms return the larger operand)
+    const float vs_f = (float)vshift;
+    const bool vfloat = (double)vs_f == vshift;
     double m0 = 0.0, m1 = 0.0, m2 = 0.0;
-    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
-        const float* dh_r = dh + r * cols;
-        const float* st_r = slope_tan + r * cols;
-        const float* as_r = aspect + r * cols;
-        unsigned char* bc_r = bin_cache + r * cols;
-        float f1 = 0.f, f2 = 0.f;  // sum y, sum y^2 of this thread over the row (<= 64 pixels): float is plenty for p0
-        unsigned fn = 0;
-        for (int c0 = 0; c0 < (int)cols; c0 += 4 * NT) {  // uniform trip count: the body holds warp-wide intrinsics
-            const int c = c0 + 4 * (int)threadIdx.x;
-            const bool in = c < (int)cols;
-            float4 d4 = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F), s4 = d4;
-            if (in) {
-                d4 = *reinterpret_cast<const float4*>(dh_r + c);
-                s4 = *reinterpret_cast<const float4*>(st_r + c);
-            }
-            const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
-            unsigned bins4 = 0xffffffffu;
-            if (!in) {
-            } else if (reuse) {
-                bins4 = *reinterpret_cast<const unsigned*>(bc_r + c);
-            } else {
-                const float4 a4 = *reinterpret_cast<const float4*>(as_r + c);
-                const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-                bins4 = 0u;
+    auto rows_loop = [&](auto vf_tag) {
+        constexpr bool VF = decltype(vf_tag)::value;
+        unsigned wn = 0;
+        for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+            const float* dh_r = dh + r * cols;
+            const float* st_r = slope_tan + r * cols;
+            const float* as_r = aspect + r * cols;
+            unsigned char* bc_r = bin_cache + r * cols;
+            float f1 = 0.f, f2 = 0.f;  // sum y, sum y^2 of this thread over the row (<= 64 pixels): float is plenty for p0
+            unsigned fn = 0;
+            for (int c0 = 0; c0 < (int)cols; c0 += 4 * NT) {  // uniform trip count: the body holds warp-wide intrinsics
+                const int c = c0 + 4 * (int)threadIdx.x;
+                const bool in = c < (int)cols;
+                float4 d4 = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F), s4 = d4;
+                unsigned bins4 = 0xffffffffu;
+                if (in) {
+                    d4 = *reinterpret_cast<const float4*>(dh_r + c);
+                    s4 = *reinterpret_cast<const float4*>(st_r + c);
+                    if (reuse) {
+                        bins4 = *reinterpret_cast<const unsigned*>(bc_r + c);
+                    } else {
+                        const float4 a4 = *reinterpret_cast<const float4*>(as_r + c);
+                        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+                        bins4 = 0u;
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    bins4 |= (isfinite(av[u]) ? (unsigned)aspect_bin(av[u], lo, hi, step, inv_step, n_bins) : 255u) << (8 * u);
-                *reinterpret_cast<unsigned*>(bc_r + c) = bins4;
-            }
-            // straight-line per-pixel work (no divergent regions: the kernel is issue-bound, ncu r02: 116 instructions
-            // per pixel with nested branches, ALU pipe 56 %): key, bin counters by predicated shared-memory atomics,
-            // bracket test
-            unsigned key[4];
-            unsigned tmask = 0u;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const unsigned b = (bins4 >> (8 * u)) & 255u;
-                const float yf = __fdiv_rn((float)((double)dv[u] - vshift), sv[u]);
-                const bool valid = b != 255u && isfinite(dv[u]) && isfinite(yf);
-                key[u] = ordered_key(yf);
-                const unsigned bb = valid ? b : (unsigned)MAXB;  // slot MAXB: bracket [0xffffffff, 0] -> never taken
-                const unsigned blo = s_lo[bb], bhi = s_hi[bb];
-                if (valid) atomicAdd(&s_total[b], 1u);
-                if (valid && key[u] < blo) atomicAdd(&s_below[b], 1u);
-                tmask |= (key[u] >= blo && key[u] <= bhi) ? (1u << u) : 0u;
-                const float yv = valid ? yf : 0.f;
-                f1 += yv, f2 = fmaf(yv, yv, f2), fn += valid;
-            }
-            if (__any_sync(0xffffffffu, tmask != 0u)) {
-                const unsigned ntk = __popc(tmask);
-                unsigned incl = ntk;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                unsigned pos = wn + incl - ntk;
-                wn += __shfl_sync(0xffffffffu, incl, 31);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (tmask & (1u << u)) {
-                        const unsigned char b = (unsigned char)((bins4 >> (8 * u)) & 255u);
-                        if (pos < WSTAGE) {
-                            s_stage[warp][pos] = key[u], s_stage_g[warp][pos] = b;
-                        } else {
-                            const unsigned long long gi = atomicAdd(&cnt[C_BNC], 1ull);
-                            if (gi < bcap) bkey[gi] = key[u], bgrp[gi] = b;
-                        }
-                        ++pos;
+                        for (int u = 0; u < 4; ++u)
+                            bins4 |= (isfinite(av[u]) ? (unsigned)aspect_bin(av[u], lo, hi, step, inv_step, n_bins) : 255u)
+                                     << (8 * u);
+                        *reinterpret_cast<unsigned*>(bc_r + c) = bins4;
                     }
-            }
-        }
-        m0 += (double)fn, m1 += (double)f1, m2 += (double)f2;
-        const unsigned n_st = min(wn, (unsigned)WSTAGE);
-        if (n_st) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&cnt[C_BNC], (unsigned long long)n_st);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            __syncwarp();
-            for (unsigned i = lane; i < n_st; i += 32)
-                if (base + i < bcap) bkey[base + i] = s_stage[warp][i], bgrp[base + i] = s_stage_g[warp][i];
-            __syncwarp();
-        }
-        wn = 0;
-    }
-    if constexpr (!SAMPLE) {
-        __syncthreads();
-        for (int k = threadIdx.x; k < n_bins; k += NT) {
-            if (s_total[k]) atomicAdd(&cnt[C_BTOTAL + k], (unsigned long long)s_total[k]);
-            if (s_below[k]) atomicAdd(&cnt[C_BBELOW + k], (unsigned long long)s_below[k]);
-        }
+                }
+                const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
+                unsigned key[4];
+                unsigned tmask = 0u;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            m0 += __shfl_xor_sync(0xffffffffu, m0, o);
-            m1 += __shfl_xor_sync(0xffffffffu, m1, o);
-            m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned b = (bins4 >> (8 * u)) & 255u;
+                    float num;
+                    if constexpr (VF) num = __fsub_rn(dv[u], vs_f);
+                    else num = (float)((double)dv[u] - vshift);
+                    const float yf = __fdiv_rn(num, sv[u]);
+                    // a finite y implies a finite dh; bin 255 = non-finite aspect
+                    const bool valid = (b != 255u) & (fabsf(yf) < CUDART_INF_F);
+                    key[u] = ordered_key(yf);
+                    const unsigned bb = valid ? b : (unsigned)MAXB;
+                    uint2 lh;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lh.x), "=r"(lh.y) : "r"(lohi_addr + 8u * bb));
+                    const bool below = key[u] < lh.x, above = key[u] > lh.y;
+                    const unsigned slot = below ? bb : (above ? bb + (unsigned)(MAXB + 1) : (unsigned)MAXB);
+                    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(cnt_addr + 4u * slot) : "memory");
+                    tmask |= (!below && !above) ? (1u << u) : 0u;
+                    const float yv = valid ? yf : 0.f;
+                    f1 += yv, f2 = fmaf(yv, yv, f2), fn += valid;
+                }
+                if (__any_sync(0xffffffffu, tmask != 0u)) {
+                    const unsigned ntk = __popc(tmask);
+                    unsigned incl = ntk;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    unsigned pos = wn + incl - ntk;
+                    wn += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (tmask & (1u << u)) {
+                            const unsigned char b = (unsigned char)((bins4 >> (8 * u)) & 255u);
+                            if (pos < WSTAGE) {
+                                s_stage[warp][pos] = key[u], s_stage_g[warp][pos] = b;
+                            } else {
+                                const unsigned long long gi = atomicAdd(&cnt[C_BNC], 1ull);
+                                if (gi < bcap) bkey[gi] = key[u], bgrp[gi] = b;
+                            }
+                            ++pos;
+                        }
+                }
+            }
+            m0 += (double)fn, m1 += (double)f1, m2 += (double)f2;
+            const unsigned n_st = min(wn, (unsigned)WSTAGE);
+            if (n_st) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&cnt[C_BNC], (unsigned long long)n_st);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                __syncwarp();
+                for (unsigned i = lane; i < n_st; i += 32)
+                    if (base + i < bcap) bkey[base + i] = s_stage[warp][i], bgrp[base + i] = s_stage_g[warp][i];
+                __syncwarp();
+            }
+            wn = 0;
         }
-        if (lane == 0 && m0 > 0.0) {
-            atomicAdd(&f64[F_M0], m0);
-            atomicAdd(&f64[F_M0 + 1], m1);
-            atomicAdd(&f64[F_M0 + 2], m2);
-        }
+    };
+    if (vfloat) rows_loop(std::true_type{});
+    else rows_loop(std::false_type{});
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_bins; k += NT) {
+        if (s_cnt[MAXB + 1 + k]) atomicAdd(&cnt[C_BTOTAL + k], (unsigned long long)s_cnt[MAXB + 1 + k]);  // ABOVE counts
+        if (s_cnt[k]) atomicAdd(&cnt[C_BBELOW + k], (unsigned long long)s_cnt[k]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m0 += __shfl_xor_sync(0xffffffffu, m0, o);
+        m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+        m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+    }
+    if (lane == 0 && m0 > 0.0) {
+        atomicAdd(&f64[F_M0], m0);
+        atomicAdd(&f64[F_M0 + 1], m1);
+        atomicAdd(&f64[F_M0 + 2], m2);
     }
 }
 
@@ -418,21 +441,45 @@ sel_hist_kernel(const unsigned* __restrict__ key, const unsigned char* __restric
     __syncthreads();
     long long total = n_seg * seg_cap;
     if (seg_count && n_seg == 1) total = (long long)min((unsigned long long)seg_cap, seg_count[0]);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        if (seg_count && n_seg > 1) {
-            const long long s = i / seg_cap, j = i - s * seg_cap;
-            if ((unsigned long long)j >= seg_count[s * seg_count_stride]) continue;
-        }
-        const unsigned k = key[i];
-        if (!k) continue;
-        const int g = grp ? (int)grp[i] : 0;
-        if (g >= G) continue;
+    auto count_one = [&](unsigned k, unsigned g) {
+        if (!k || g >= (unsigned)G) return;
         const unsigned d = (k >> shift) & 255u, km = k & mask;
         // while both queries of a group still share their prefix only row 2g is counted (the pick kernel reads it for
         // both); pass 0 (mask == 0) matches every key whatever an earlier select left in `prefix`
         const unsigned p0 = s_pre[2 * g], p1 = s_pre[2 * g + 1];
         if (km == p0) atomicAdd(&sh[(2 * g) * 256 + d], 1u);
         if (km == p1 && p1 != p0) atomicAdd(&sh[(2 * g + 1) * 256 + d], 1u);
+    };
+    // four entries per thread and trip, two trips in flight (the scalar loop was bound by the latency of its dependent
+    // loads: 60 us for 8 M entries, ncu r02)
+    const bool vec = (reinterpret_cast<uintptr_t>(key) % 16 == 0) && (!grp || reinterpret_cast<uintptr_t>(grp) % 4 == 0) &&
+                     (n_seg == 1 || seg_cap % 4 == 0);
+    const long long nvec = vec ? total / 4 : 0;
+    const uint4* key4 = reinterpret_cast<const uint4*>(key);
+    const uchar4* grp4 = reinterpret_cast<const uchar4*>(grp);
+#pragma unroll 2
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x) {
+        unsigned live = 4;
+        if (seg_count && n_seg > 1) {
+            const long long s = (4 * v) / seg_cap, j = 4 * v - s * seg_cap;
+            const unsigned long long c = seg_count[s * seg_count_stride];
+            live = (unsigned long long)j >= c ? 0u : (unsigned)min(4ull, c - (unsigned long long)j);
+        }
+        if (!live) continue;
+        const uint4 k4 = key4[v];
+        const uchar4 g4 = grp ? grp4[v] : make_uchar4(0, 0, 0, 0);
+        count_one(k4.x, g4.x);
+        if (live > 1) count_one(k4.y, g4.y);
+        if (live > 2) count_one(k4.z, g4.z);
+        if (live > 3) count_one(k4.w, g4.w);
+    }
+    for (long long i = 4 * nvec + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        if (seg_count && n_seg > 1) {
+            const long long s = i / seg_cap, j = i - s * seg_cap;
+            if ((unsigned long long)j >= seg_count[s * seg_count_stride]) continue;
+        }
+        count_one(key[i], grp ? (unsigned)grp[i] : 0u);
     }
     __syncthreads();
     for (int k = threadIdx.x; k < n_cnt; k += blockDim.x)
@@ -444,10 +491,12 @@ sel_hist_kernel(const unsigned* __restrict__ key, const unsigned char* __restric
 //   sampled chunk were fully correlated; outputs the two keys.
 // mode 1 (median): ranks (N-1)/2 - B and N/2 - B inside the compact buffer, N = ext_total[g] elements of the group in
 //   the population, B = ext_below[g] of them below the bracket; outputs the mean of the two middle values (float64).
+// mode 2: like 1, but ext_total[g] arrives as the count ABOVE the bracket: N = above + B + (entries of the group in the
+//   buffer); N is written back to ext_total[g].
 __global__ void __launch_bounds__(256)
 sel_pick_kernel(int G, int mode, int pass, int last_pass, int shift, unsigned mask, unsigned* __restrict__ hist,
                 unsigned* __restrict__ prefix, unsigned long long* __restrict__ below, long long* __restrict__ rank,
-                const unsigned long long* __restrict__ ext_total, const unsigned long long* __restrict__ ext_below,
+                unsigned long long* __restrict__ ext_total, const unsigned long long* __restrict__ ext_below,
                 unsigned* __restrict__ out_lo, unsigned* __restrict__ out_hi, double* __restrict__ out_val,
                 unsigned long long* __restrict__ flags, unsigned long long miss_bit) {
     // one warp per GROUP: it serves the group's two queries in turn (query 1 reads query 0's histogram while the two
@@ -459,6 +508,7 @@ sel_pick_kernel(int G, int mode, int pass, int last_pass, int shift, unsigned ma
     const bool shared_row = pass == 0 || pm0 == pm1;
     unsigned keyq[2] = {0u, 0u};
     long long rkq[2] = {-1, -1};
+    long long n_pop = -1;
     for (int q = 0; q < 2; ++q) {
         const int t = 2 * g + q;
         const unsigned* h = hist + (size_t)(shared_row ? 2 * g : t) * 256;
@@ -488,7 +538,10 @@ sel_pick_kernel(int G, int mode, int pass, int last_pass, int shift, unsigned ma
                     rk = q ? min(m - 1, m / 2 + margin) : max(0ll, (m - 1) / 2 - margin);
                 }
             } else {
-                const long long N = (long long)ext_total[g], B = (long long)ext_below[g];
+                // mode 2: ext_total holds the count ABOVE the bracket; the buffer's own total completes the population
+                const long long B = (long long)ext_below[g];
+                const long long N = mode == 2 ? (long long)ext_total[g] + B + (long long)tot : (long long)ext_total[g];
+                n_pop = N;
                 if (N == 0) {
                     rk = -1;
                 } else {
@@ -530,6 +583,7 @@ sel_pick_kernel(int G, int mode, int pass, int last_pass, int shift, unsigned ma
         keyq[q] = pre, rkq[q] = rk;
     }
     __syncwarp();
+    if (mode == 2 && pass == 0 && lane == 0) ext_total[g] = (unsigned long long)n_pop;  // callers read the bin totals
     // zero both histogram rows for the next pass / the next select
 #pragma unroll
     for (int j = 0; j < 16; ++j) hist[(size_t)(2 * g) * 256 + lane * 16 + j] = 0u;
@@ -545,6 +599,226 @@ sel_pick_kernel(int G, int mode, int pass, int last_pass, int shift, unsigned ma
         out_val[g] = (rkq[0] >= 0 && rkq[1] >= 0)
                          ? 0.5 * ((double)key_to_float(keyq[0]) + (double)key_to_float(keyq[1]))
                          : CUDART_NAN;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One-time preparation of a fit: `_nuth_kaab_aux_vars` (np.gradient in NumPy's float32 op order, slope_tan, aspect,
+// affine.py:412-474, 578-579 -- same expressions as xbn::nk_aux_kernel) fused with the validity mask of
+// `_preprocess_rst_pts_subsample` (inlier & finite(ref, tba, slope_tan, aspect), base.py:653-661), its count, and the
+// aspect range over the valid pixels.  17 B/px in one pass instead of the aux pass + nine elementwise torch passes.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+nk_prepare_kernel(const float* __restrict__ z, long long rows_buf, long long cols, long long ld, int top_is_border,
+                  int bottom_is_border, long long row_begin, long long row_end, const float* __restrict__ tba,
+                  long long tba_ld, const unsigned char* __restrict__ inlier, float* __restrict__ slope_tan,
+                  float* __restrict__ aspect, unsigned char* __restrict__ sub_mask, unsigned long long* __restrict__ n_valid,
+                  unsigned* __restrict__ asp_minmax) {
+    unsigned lmin = 0xffffffffu, lmax = 0u;
+    unsigned cnt = 0;
+    for (long long r = row_begin + blockIdx.x; r < row_end; r += gridDim.x) {
+        const float* zr = z + r * ld;
+        const bool top = (r == 0) && top_is_border;
+        const bool bot = (r == rows_buf - 1) && bottom_is_border;
+        for (long long c = threadIdx.x; c < cols; c += NT) {
+            float gx, gy;
+            if (c == 0)
+                gx = __fsub_rn(zr[1], zr[0]);
+            else if (c == cols - 1)
+                gx = __fsub_rn(zr[c], zr[c - 1]);
+            else
+                gx = __fmul_rn(__fsub_rn(zr[c + 1], zr[c - 1]), 0.5f);
+            if (top)
+                gy = __fsub_rn(zr[ld + c], zr[c]);
+            else if (bot)
+                gy = __fsub_rn(zr[c], zr[c - ld]);
+            else
+                gy = __fmul_rn(__fsub_rn(zr[ld + c], zr[c - ld]), 0.5f);
+            float st = __fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
+            const float asp = __fadd_rn(atan2f(-gx, gy), 3.14159274101257324f);
+            if (fabsf(st) <= 1e-8f) st = CUDART_NAN_F;
+            const long long o = (r - row_begin) * cols + c;
+            slope_tan[o] = st;
+            aspect[o] = asp;
+            const bool ok = (!inlier || inlier[o]) && isfinite(zr[c]) && isfinite(tba[(r - row_begin) * tba_ld + c]) &&
+                            isfinite(st) && isfinite(asp);
+            sub_mask[o] = ok ? 1 : 0;
+            if (ok) {
+                const unsigned ab = __float_as_uint(asp);  // aspect >= 0: the bit pattern is monotonic
+                lmin = min(lmin, ab), lmax = max(lmax, ab);
+                ++cnt;
+            }
+        }
+    }
+    lmin = __reduce_min_sync(0xffffffffu, lmin);
+    lmax = __reduce_max_sync(0xffffffffu, lmax);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicMin(&asp_minmax[0], lmin);
+        atomicMax(&asp_minmax[1], lmax);
+        atomicAdd(n_valid, (unsigned long long)cnt);
+    }
+}
+
+// The same, four pixels per thread (cols % 4 == 0, 16-byte aligned rows): vector loads of the three reference rows, the
+// to-be-aligned row and the inlier bytes, vector stores of the three outputs.  Every warp also records its smallest /
+// largest valid aspect with one pixel that attains it: rec[4 w .. 4 w + 3] = {min bits, position, max bits, position}
+// (0xffffffff / 0 when the warp saw no valid pixel), from which nk_candidates_kernel assembles the range candidates
+// without another pass over the aspect plane.
+__global__ void __launch_bounds__(NT)
+nk_prepare_vec4_kernel(const float* __restrict__ z, long long rows_buf, long long cols, long long ld, int top_is_border,
+                       int bottom_is_border, long long row_begin, long long row_end, const float* __restrict__ tba,
+                       long long tba_ld, const unsigned char* __restrict__ inlier, float* __restrict__ slope_tan,
+                       float* __restrict__ aspect, unsigned char* __restrict__ sub_mask,
+                       unsigned long long* __restrict__ n_valid, unsigned* __restrict__ rec) {
+    unsigned lmin = 0xffffffffu, lmax = 0u, pmin = 0u, pmax = 0u;
+    unsigned cnt = 0;
+    for (long long r = row_begin + blockIdx.x; r < row_end; r += gridDim.x) {
+        const float* zr = z + r * ld;
+        const bool top = (r == 0) && top_is_border;
+        const bool bot = (r == rows_buf - 1) && bottom_is_border;
+        for (long long c = 4ll * threadIdx.x; c < cols; c += 4ll * NT) {
+            const float4 m4 = *reinterpret_cast<const float4*>(zr + c);
+            const float4 u4 = top ? m4 : *reinterpret_cast<const float4*>(zr - ld + c);
+            const float4 d4 = bot ? m4 : *reinterpret_cast<const float4*>(zr + ld + c);
+            const float4 t4 = *reinterpret_cast<const float4*>(tba + (r - row_begin) * tba_ld + c);
+            const long long o = (r - row_begin) * cols + c;
+            const uchar4 i4 = inlier ? *reinterpret_cast<const uchar4*>(inlier + o) : make_uchar4(1, 1, 1, 1);
+            const float w[6] = {c > 0 ? zr[c - 1] : 0.f, m4.x, m4.y, m4.z, m4.w, c + 4 < cols ? zr[c + 4] : 0.f};
+            const float up[4] = {u4.x, u4.y, u4.z, u4.w}, dn[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float tb[4] = {t4.x, t4.y, t4.z, t4.w};
+            const unsigned char in4[4] = {i4.x, i4.y, i4.z, i4.w};
+            float st4[4], as4[4];
+            unsigned char mk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long long col = c + k;
+                float gx, gy;
+                if (col == 0)
+                    gx = __fsub_rn(w[k + 2], w[k + 1]);
+                else if (col == cols - 1)
+                    gx = __fsub_rn(w[k + 1], w[k]);
+                else
+                    gx = __fmul_rn(__fsub_rn(w[k + 2], w[k]), 0.5f);
+                if (top)
+                    gy = __fsub_rn(dn[k], w[k + 1]);
+                else if (bot)
+                    gy = __fsub_rn(w[k + 1], up[k]);
+                else
+                    gy = __fmul_rn(__fsub_rn(dn[k], up[k]), 0.5f);
+                float st = __fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
+                const float asp = __fadd_rn(atan2f(-gx, gy), 3.14159274101257324f);
+                if (fabsf(st) <= 1e-8f) st = CUDART_NAN_F;
+                st4[k] = st, as4[k] = asp;
+                const bool ok = in4[k] && isfinite(w[k + 1]) && isfinite(tb[k]) && isfinite(st) && isfinite(asp);
+                mk[k] = ok ? 1 : 0;
+                if (ok) {
+                    const unsigned ab = __float_as_uint(asp);  // aspect >= 0: the bit pattern is monotonic
+                    if (ab < lmin) lmin = ab, pmin = (unsigned)(o + k);
+                    if (ab >= lmax) lmax = ab, pmax = (unsigned)(o + k);
+                    ++cnt;
+                }
+            }
+            *reinterpret_cast<float4*>(slope_tan + o) = make_float4(st4[0], st4[1], st4[2], st4[3]);
+            *reinterpret_cast<float4*>(aspect + o) = make_float4(as4[0], as4[1], as4[2], as4[3]);
+            *reinterpret_cast<uchar4*>(sub_mask + o) = make_uchar4(mk[0], mk[1], mk[2], mk[3]);
+        }
+    }
+    const unsigned wmin = __reduce_min_sync(0xffffffffu, lmin), wmax = __reduce_max_sync(0xffffffffu, lmax);
+    const unsigned total = __reduce_add_sync(0xffffffffu, cnt);
+    const unsigned bmin = __ballot_sync(0xffffffffu, cnt && lmin == wmin), bmax = __ballot_sync(0xffffffffu, cnt && lmax == wmax);
+    const unsigned qmin = __shfl_sync(0xffffffffu, pmin, bmin ? __ffs(bmin) - 1 : 0);
+    const unsigned qmax = __shfl_sync(0xffffffffu, pmax, bmax ? __ffs(bmax) - 1 : 0);
+    if ((threadIdx.x & 31) == 0) {
+        unsigned* q = rec + 4ll * ((long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5));
+        q[0] = total ? wmin : 0xffffffffu, q[1] = qmin, q[2] = total ? wmax : 0u, q[3] = qmax;
+        if (total) atomicAdd(n_valid, (unsigned long long)total);
+    }
+}
+
+// one CTA: global aspect range of the warps' records and up to RC_K positions attaining each end -> rc (layout below)
+__global__ void __launch_bounds__(1024) nk_candidates_kernel(const unsigned* __restrict__ rec, int n_rec,
+                                                              unsigned* __restrict__ rc) {
+    __shared__ unsigned s_min, s_max, s_nmin, s_nmax;
+    if (threadIdx.x == 0) s_min = 0xffffffffu, s_max = 0u, s_nmin = 0u, s_nmax = 0u;
+    __syncthreads();
+    unsigned lmin = 0xffffffffu, lmax = 0u;
+    for (int i = threadIdx.x; i < n_rec; i += blockDim.x) lmin = min(lmin, rec[4 * i]), lmax = max(lmax, rec[4 * i + 2]);
+    lmin = __reduce_min_sync(0xffffffffu, lmin), lmax = __reduce_max_sync(0xffffffffu, lmax);
+    if ((threadIdx.x & 31) == 0) atomicMin(&s_min, lmin), atomicMax(&s_max, lmax);
+    __syncthreads();
+    const unsigned gmin = s_min, gmax = s_max;
+    if (gmin != 0xffffffffu)  // at least one valid pixel
+        for (int i = threadIdx.x; i < n_rec; i += blockDim.x) {
+            if (rec[4 * i] == gmin) {
+                const unsigned k = atomicAdd(&s_nmin, 1u);
+                if (k < (unsigned)64) rc[4 + k] = rec[4 * i + 1];
+            }
+            if (rec[4 * i + 2] == gmax && rec[4 * i] != 0xffffffffu) {
+                const unsigned k = atomicAdd(&s_nmax, 1u);
+                if (k < (unsigned)64) rc[4 + 64 + k] = rec[4 * i + 3];
+            }
+        }
+    __syncthreads();
+    if (threadIdx.x == 0) rc[0] = gmin, rc[1] = gmax, rc[2] = min(s_nmin, 64u), rc[3] = min(s_nmax, 64u);
+}
+
+// Positions of (up to RC_K) valid pixels that attain the static aspect minimum / maximum.  The aspect range of an
+// iteration is taken over the pixels with a finite dh -- a subset of the valid ones that only differs along the shifted
+// raster edge -- so it equals the static range whenever one of these pixels still has a finite dh, which
+// nkf_range_check_kernel verifies in O(RC_K) instead of re-reading the aspect plane in every dh pass.
+// rc layout (uint32): [0] min bits, [1] max bits, [2] n_min, [3] n_max, [4 .. 4+K) min positions, [4+K .. 4+2K) max.
+constexpr int RC_K = 64;
+__global__ void __launch_bounds__(NT)
+nk_extremes_kernel(const float* __restrict__ aspect, const unsigned char* __restrict__ sub_mask, long long n,
+                   unsigned* __restrict__ rc) {
+    const unsigned amin = rc[0], amax = rc[1];
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+        if (!sub_mask[i]) continue;
+        const unsigned ab = __float_as_uint(aspect[i]);
+        if (ab == amin && *reinterpret_cast<volatile unsigned*>(rc + 2) < (unsigned)RC_K) {
+            const unsigned k = atomicAdd(&rc[2], 1u);
+            if (k < (unsigned)RC_K) rc[4 + k] = (unsigned)i;
+        }
+        if (ab == amax && *reinterpret_cast<volatile unsigned*>(rc + 3) < (unsigned)RC_K) {
+            const unsigned k = atomicAdd(&rc[3], 1u);
+            if (k < (unsigned)RC_K) rc[4 + RC_K + k] = (unsigned)i;
+        }
+    }
+}
+
+// one warp: is the static aspect range still attained among the finite dh?  Otherwise cnt[C_RFALL] = 1 and
+// nkf_range_full_kernel (always launched; returns at once when the flag is clear) reduces the range over the raster.
+__global__ void nkf_range_check_kernel(const float* __restrict__ dh, const unsigned* __restrict__ rc,
+                                       unsigned* __restrict__ keys, unsigned long long* __restrict__ cnt) {
+    const int lane = threadIdx.x;
+    const unsigned n_min = min(rc[2], (unsigned)RC_K), n_max = min(rc[3], (unsigned)RC_K);
+    bool okmin = false, okmax = false;
+    for (unsigned k = lane; k < n_min; k += 32) okmin |= isfinite(dh[rc[4 + k]]);
+    for (unsigned k = lane; k < n_max; k += 32) okmax |= isfinite(dh[rc[4 + RC_K + k]]);
+    okmin = __any_sync(0xffffffffu, okmin), okmax = __any_sync(0xffffffffu, okmax);
+    if (lane == 0) {
+        if (okmin && okmax) keys[K_ASPMIN] = rc[0], keys[K_ASPMAX] = rc[1];
+        else cnt[C_RFALL] = 1ull;
+    }
+}
+__global__ void __launch_bounds__(NT)
+nkf_range_full_kernel(const float* __restrict__ dh, const float* __restrict__ aspect, long long n,
+                      unsigned* __restrict__ keys, const unsigned long long* __restrict__ cnt) {
+    if (cnt[C_RFALL] == 0ull) return;
+    unsigned lmin = 0xffffffffu, lmax = 0u;
+    bool any = false;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT)
+        if (isfinite(dh[i])) {
+            const unsigned ab = __float_as_uint(aspect[i]);
+            lmin = min(lmin, ab), lmax = max(lmax, ab), any = true;
+        }
+    lmin = __reduce_min_sync(0xffffffffu, lmin);
+    lmax = __reduce_max_sync(0xffffffffu, lmax);
+    any = __any_sync(0xffffffffu, any);
+    if ((threadIdx.x & 31) == 0 && any) {
+        atomicMin(&keys[K_ASPMIN], lmin);
+        atomicMax(&keys[K_ASPMAX], lmax);
     }
 }
 
@@ -580,6 +854,58 @@ static int grid_rows(long long n_rows, int per_sm) {
 extern "C" {
 #pragma GCC visibility push(default)
 
+int xb_nk_prepare(const float* ref_dev, int64_t rows_buf, int64_t cols, int64_t ld, int top_is_border,
+                  int bottom_is_border, int64_t row_begin, int64_t row_end, const float* tba_dev, int64_t tba_ld,
+                  const uint8_t* inlier_dev, float* slope_tan_dev, float* aspect_dev, uint8_t* sub_mask_dev,
+                  unsigned long long* n_valid_dev, uint32_t* range_cand_dev, void* stream) {
+    if (!ref_dev || !tba_dev || !slope_tan_dev || !aspect_dev || !sub_mask_dev || !n_valid_dev || !range_cand_dev ||
+        rows_buf < 2 || cols < 2 || ld < cols || tba_ld < cols || row_begin < 0 || row_end > rows_buf ||
+        row_begin > row_end) {
+        xb_set_error("bad arguments to xb_nk_prepare (np.gradient needs at least 2 rows and 2 columns)");
+        return XB_ERR_INVALID;
+    }
+    if ((!top_is_border && row_begin < 1) || (!bottom_is_border && row_end > rows_buf - 1)) {
+        xb_set_error("xb_nk_prepare: interior shards need one halo row above/below the output rows");
+        return XB_ERR_INVALID;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const uint32_t init[4] = {0xffffffffu, 0u, 0u, 0u};
+    XB_CUDA_CHECK(cudaMemcpyAsync(range_cand_dev, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    XB_CUDA_CHECK(cudaMemsetAsync(n_valid_dev, 0, sizeof(unsigned long long), st));
+    const long long rows = row_end - row_begin;
+    if (rows == 0) return XB_OK;
+    const bool vec4 = cols % 4 == 0 && ld % 4 == 0 && tba_ld % 4 == 0 && rows * cols < (1ll << 32) &&
+                      ((reinterpret_cast<uintptr_t>(ref_dev) | reinterpret_cast<uintptr_t>(tba_dev) |
+                        reinterpret_cast<uintptr_t>(slope_tan_dev) | reinterpret_cast<uintptr_t>(aspect_dev)) % 16 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(sub_mask_dev) | reinterpret_cast<uintptr_t>(inlier_dev)) % 4 == 0);
+    if (vec4) {
+        const int grid = xbf::grid_rows(rows, 8);
+        const int n_rec = grid * (xbf::NT / 32);
+        unsigned* rec = nullptr;
+        XB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&rec), (size_t)n_rec * 4 * sizeof(unsigned), st));
+        xbf::nk_prepare_vec4_kernel<<<grid, xbf::NT, 0, st>>>(ref_dev, rows_buf, cols, ld, top_is_border, bottom_is_border,
+                                                              row_begin, row_end, tba_dev, tba_ld, inlier_dev,
+                                                              slope_tan_dev, aspect_dev, sub_mask_dev, n_valid_dev, rec);
+        xbf::nk_candidates_kernel<<<1, 1024, 0, st>>>(rec, n_rec, range_cand_dev);
+        XB_CUDA_CHECK(cudaGetLastError());
+        XB_CUDA_CHECK(cudaFreeAsync(rec, st));
+        xb_count_launch(2);
+        return XB_OK;
+    }
+    xbf::nk_prepare_kernel<<<xbf::grid_rows(rows, 8), xbf::NT, 0, st>>>(
+        ref_dev, rows_buf, cols, ld, top_is_border, bottom_is_border, row_begin, row_end, tba_dev, tba_ld, inlier_dev,
+        slope_tan_dev, aspect_dev, sub_mask_dev, n_valid_dev, range_cand_dev);
+    XB_CUDA_CHECK(cudaGetLastError());
+    xb_count_launch(1);
+    if (rows * cols < (1ll << 32)) {
+        xbf::nk_extremes_kernel<<<xbf::grid_rows((rows * cols + xbf::NT - 1) / xbf::NT, 8), xbf::NT, 0, st>>>(
+            aspect_dev, sub_mask_dev, rows * cols, range_cand_dev);
+        XB_CUDA_CHECK(cudaGetLastError());
+        xb_count_launch(1);
+    }
+    return XB_OK;
+}
+
 int xb_nkf_layout(int32_t* out) {
     if (!out) return XB_ERR_INVALID;
     const int v[16] = {xbf::MAXB,    xbf::C_SIZE,  xbf::K_SIZE,  xbf::F_SIZE, xbf::C_NFIN,   xbf::C_GBELOW,
@@ -606,7 +932,7 @@ int xb_nkf_dh(int sample, const float* ref_dev, const float* tba_dev, const uint
               int64_t tba_rows_total, double dx_px, double dy_px, float* dh_dev, uint32_t* sample_dev, int stride,
               uint32_t seed, unsigned long long* cnt_dev, uint32_t* keys_dev, uint32_t* gcompact_dev, uint64_t gcap,
               void* stream) {
-    if (!ref_dev || !tba_dev || !sub_mask_dev || !aspect_dev || !cnt_dev || !keys_dev || rows <= 0 || cols < 4 ||
+    if (!ref_dev || !tba_dev || !sub_mask_dev || !cnt_dev || !keys_dev || rows <= 0 || cols < 4 ||
         cols % 4 || ld % 4 || ld < cols || tba_ld < cols || stride < 1 || (sample ? !sample_dev : (!dh_dev || !gcompact_dev)) ||
         ((reinterpret_cast<uintptr_t>(ref_dev) | reinterpret_cast<uintptr_t>(aspect_dev) |
           reinterpret_cast<uintptr_t>(dh_dev) | reinterpret_cast<uintptr_t>(sample_dev)) % 16) ||
@@ -674,11 +1000,11 @@ int xb_nkf_y(int sample, const float* dh_dev, const float* slope_tan_dev, const 
 
 int xb_nkf_select(const uint32_t* key_dev, const uint8_t* grp_dev, int64_t n_seg, int64_t seg_cap,
                   const unsigned long long* seg_count_dev, int64_t seg_count_stride, int n_groups, int mode,
-                  const unsigned long long* ext_total_dev, const unsigned long long* ext_below_dev, uint32_t* out_lo_dev,
+                  unsigned long long* ext_total_dev, const unsigned long long* ext_below_dev, uint32_t* out_lo_dev,
                   uint32_t* out_hi_dev, double* out_val_dev, unsigned long long* flags_dev, uint64_t miss_bit,
                   uint32_t* hist_dev, uint32_t* prefix_dev, unsigned long long* below_dev, long long* rank_dev,
                   void* stream) {
-    if (!key_dev || n_seg < 1 || seg_cap < 1 || n_groups < 1 || n_groups > xbf::MAXB || (mode != 0 && mode != 1) ||
+    if (!key_dev || n_seg < 1 || seg_cap < 1 || n_groups < 1 || n_groups > xbf::MAXB || (mode < 0 || mode > 2) ||
         !hist_dev || !prefix_dev || !below_dev || !rank_dev || !flags_dev ||
         (mode == 0 ? (!out_lo_dev || !out_hi_dev) : (!out_val_dev || !ext_total_dev || !ext_below_dev))) {
         xb_set_error("bad arguments to xb_nkf_select");
@@ -730,7 +1056,8 @@ int xb_nkf_iteration(const float* ref_dev, const float* tba_dev, const uint8_t* 
                      uint32_t* sample_dev, uint8_t* sgrp_dev, int64_t ns, int stride, uint32_t seed,
                      uint32_t* gcompact_dev, uint64_t gcap, uint32_t* bkey_dev, uint8_t* bgrp_dev, uint64_t bcap,
                      unsigned long long* cnt_dev, uint32_t* keys_dev, double* f64_dev, uint32_t* hist_dev,
-                     uint32_t* prefix_dev, unsigned long long* below_dev, long long* rank_dev, void* stream) {
+                     uint32_t* prefix_dev, unsigned long long* below_dev, long long* rank_dev,
+                     const uint32_t* range_cand_dev, void* stream) {
     using namespace xbf;
     int rc = xb_nkf_reset(cnt_dev, keys_dev, f64_dev, hist_dev, stream);
     if (rc) return rc;
@@ -740,9 +1067,18 @@ int xb_nkf_iteration(const float* ref_dev, const float* tba_dev, const uint8_t* 
     rc = xb_nkf_select(sample_dev, nullptr, 1, ns, nullptr, 1, 1, 0, nullptr, nullptr, keys_dev + K_GLO, keys_dev + K_GHI,
                        nullptr, cnt_dev + C_FLAGS, FLAG_GMISS, hist_dev, prefix_dev, below_dev, rank_dev, stream);
     if (rc) return rc;
-    rc = xb_nkf_dh(0, ref_dev, tba_dev, sub_mask_dev, aspect_dev, rows, cols, ld, tba_ld, tba_row0, tba_rows_total, dx_px,
-                   dy_px, dh_dev, sample_dev, stride, seed, cnt_dev, keys_dev, gcompact_dev, gcap, stream);
+    const bool rcheck = range_cand_dev != nullptr && rows * cols < (1ll << 32);
+    rc = xb_nkf_dh(0, ref_dev, tba_dev, sub_mask_dev, rcheck ? nullptr : aspect_dev, rows, cols, ld, tba_ld, tba_row0,
+                   tba_rows_total, dx_px, dy_px, dh_dev, sample_dev, stride, seed, cnt_dev, keys_dev, gcompact_dev, gcap,
+                   stream);
     if (rc) return rc;
+    if (rcheck) {
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        nkf_range_check_kernel<<<1, 32, 0, st>>>(dh_dev, range_cand_dev, keys_dev, cnt_dev);
+        nkf_range_full_kernel<<<grid_rows(rows, 4), NT, 0, st>>>(dh_dev, aspect_dev, rows * cols, keys_dev, cnt_dev);
+        XB_CUDA_CHECK(cudaGetLastError());
+        xb_count_launch(2);
+    }
     rc = xb_nkf_range(keys_dev, f64_dev, stream);
     if (rc) return rc;
     rc = xb_nkf_select(gcompact_dev, nullptr, 1, (int64_t)gcap, cnt_dev + C_GNC, 1, 1, 1, cnt_dev + C_NFIN,
@@ -759,7 +1095,7 @@ int xb_nkf_iteration(const float* ref_dev, const float* tba_dev, const uint8_t* 
     rc = xb_nkf_y(0, dh_dev, slope_tan_dev, aspect_dev, bin_cache_dev, rows, cols, n_bins, sample_dev, sgrp_dev, stride,
                   seed ^ 0x5BD1E995u, cnt_dev, keys_dev, f64_dev, bkey_dev, bgrp_dev, bcap, stream);
     if (rc) return rc;
-    rc = xb_nkf_select(bkey_dev, bgrp_dev, 1, (int64_t)bcap, cnt_dev + C_BNC, 1, n_bins, 1, cnt_dev + C_BTOTAL,
+    rc = xb_nkf_select(bkey_dev, bgrp_dev, 1, (int64_t)bcap, cnt_dev + C_BNC, 1, n_bins, 2, cnt_dev + C_BTOTAL,
                        cnt_dev + C_BBELOW, nullptr, nullptr, f64_dev + F_MED, cnt_dev + C_FLAGS, FLAG_BMISS, hist_dev,
                        prefix_dev, below_dev, rank_dev, stream);
     if (rc) return rc;

@@ -191,7 +191,7 @@ def sharded_nuth_kaab(ref_rows: torch.Tensor, tba_rows: torch.Tensor, inlier_row
         ref_halo, tba_halo = (None, None), (None, None)
     state = coreg._NKState(ref_rows, tba_rows, inlier_rows, group=group, ref_halo=ref_halo, tba_halo=tba_halo)
     state.sharded = world > 1
-    n_valid = state.valid.sum().to(torch.int64).reshape(1)
+    n_valid = state._n_valid_t.clone()
     if world > 1:
         dist.all_reduce(n_valid, group=group)
     if int(n_valid.item()) == 0:
