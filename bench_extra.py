@@ -172,8 +172,9 @@ def bench_nuthkaab(args) -> dict:
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": algo / dt / 1e9, "peak": peak * world, "unit": "GB/s",
                      "frac": algo / dt / 1e9 / (peak * world),
-                     "note": "algorithmic minimum 12 B/px (aux) + 16 B/px/iteration; the radix-select medians stream "
-                             "~7 passes per iteration (DESIGN.md K3)"},
+                     "note": "algorithmic minimum 12 B/px (aux) + 16 B/px/iteration; the bracketed exact selection "
+                             "streams two full passes (dh 13 B/px, y 9 B/px) + a 4 M-pixel sample per iteration, "
+                             "host curve_fit included in the time (DESIGN.md K3)"},
         "cpu_baseline": {"value": cs * cs * 10 / tcpu / 1e6, "unit": "Mpixel*iter/s", "cores": 1, "kind": "port",
                          "sample": f"{cs}^2 crop of the same pair, 10 iterations ({tcpu:.1f} s)",
                          "what": "oracle/nk_oracle.py (NumPy/SciPy restatement of affine.py:477-609, pinned to reference "

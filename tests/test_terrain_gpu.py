@@ -384,6 +384,23 @@ def test_fractal_roughness_known_answers(xb) -> None:
         assert np.round(xb.terrain.fractal_roughness(dem)[6, 6], 3) == np.float32(expect)
 
 
+def test_three_cycle_request_keeps_requested_order(xb, G) -> None:
+    """A request whose category permutation is a 3-cycle (windowed, frequency, surface): outs[i] is attribute[i].  The
+    reference's re-ordering (terrain.py:648-656) applies the permutation instead of its inverse and would return
+    (texture_shading, slope, roughness) here -- a documented, deliberate deviation (terrain.py docstring,
+    INTEGRATION.md section 6)."""
+    dem = G["in|fractal"]
+    req = ["roughness", "texture_shading", "slope"]
+    outs = xb.terrain.get_terrain_attribute(dem, req, resolution=5.0)
+    assert np.array_equal(outs[0], xb.terrain.roughness(dem), equal_nan=True)
+    assert np.array_equal(outs[1], xb.terrain.texture_shading(dem), equal_nan=True)
+    assert np.array_equal(outs[2], xb.terrain.slope(dem, resolution=5.0), equal_nan=True)
+    # what the reference's index expression yields for this request (pure list logic, no reference import needed)
+    grouped = ["slope", "roughness", "texture_shading"]  # surface + windowed + frequency (terrain.py:647)
+    ref_order = [grouped[req.index(a)] for a in grouped]
+    assert ref_order == ["texture_shading", "slope", "roughness"] and ref_order != req
+
+
 def test_mixed_request_all_paths(xb, G) -> None:
     """One call mixing the fused kernel, the 3x3 rugosity special case, a generic window and fractal roughness keeps the
     request order and equals the single-attribute calls (terrain.py:651-658)."""

@@ -20,6 +20,14 @@ from .terrain import get_terrain_attribute  # noqa: F401
 
 __version__ = "0.1.0"
 
+_ORIGINALS: dict[tuple[str, str], object] = {}  # (module, name) -> what install() replaced
+
+
+def _rebind(module: object, name: str, new: object) -> None:
+    key = (getattr(module, "__name__", str(module)), name)
+    _ORIGINALS.setdefault(key, getattr(module, name))
+    setattr(module, name, new)
+
 
 def install() -> None:
     """Rebind the reference's engine seams to the B200 engine (integration mode ii).
@@ -43,8 +51,8 @@ def install() -> None:
     from .surfit import _get_surface_attributes
     from .window import _get_windowed_indexes
 
-    ref_terrain._get_surface_attributes = _get_surface_attributes
-    ref_terrain._get_windowed_indexes = _get_windowed_indexes
+    _rebind(ref_terrain, "_get_surface_attributes", _get_surface_attributes)
+    _rebind(ref_terrain, "_get_windowed_indexes", _get_windowed_indexes)
 
     try:
         ref_affine = importlib.import_module("xdem.coreg.affine")
@@ -53,7 +61,8 @@ def install() -> None:
     if ref_affine is not None and hasattr(ref_affine, "nuth_kaab"):
         from . import coreg
 
-        ref_affine.nuth_kaab = coreg.make_reference_hook(ref_affine.nuth_kaab)
+        original = _ORIGINALS.get((ref_affine.__name__, "nuth_kaab"), ref_affine.nuth_kaab)  # idempotent install()
+        _rebind(ref_affine, "nuth_kaab", coreg.make_reference_hook(original))
 
     try:
         ref_ss = importlib.import_module("xdem.spatialstats")
@@ -62,6 +71,15 @@ def install() -> None:
     if ref_ss is not None and hasattr(ref_ss, "_get_pdist_empirical_variogram"):
         from . import spatialstats as xs
 
-        ref_ss._get_pdist_empirical_variogram = xs._get_pdist_empirical_variogram
-        if hasattr(xs, "_get_cdist_empirical_variogram"):
-            ref_ss._get_cdist_empirical_variogram = xs._get_cdist_empirical_variogram
+        _rebind(ref_ss, "_get_pdist_empirical_variogram", xs._get_pdist_empirical_variogram)
+        if hasattr(ref_ss, "_get_cdist_empirical_variogram"):
+            _rebind(ref_ss, "_get_cdist_empirical_variogram", xs._get_cdist_empirical_variogram)
+
+
+def uninstall() -> None:
+    """Undo ``install()``: put the reference's own functions back."""
+    import importlib
+
+    for (mod_name, name), original in list(_ORIGINALS.items()):
+        setattr(importlib.import_module(mod_name), name, original)
+    _ORIGINALS.clear()

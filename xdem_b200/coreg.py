@@ -146,7 +146,7 @@ class _NKState:
                                        self.tba_buf.stride(0), self.tba_row0, self.tba_buf.shape[0], float(dx_px),
                                        float(dy_px), self.dh.data_ptr(), mm.data_ptr(), cnt.data_ptr(), self.stream))
         mm64 = mm.to(torch.int64) & 0xFFFFFFFF
-        if self.sharded and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+        if self.sharded and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             lo_t, hi_t = mm64[0:1].clone(), mm64[1:2].clone()
             dist.all_reduce(lo_t, op=dist.ReduceOp.MIN, group=self.group)
             dist.all_reduce(hi_t, op=dist.ReduceOp.MAX, group=self.group)
@@ -207,7 +207,8 @@ class _NKState:
         names = ["MAXB", "C_SIZE", "K_SIZE", "F_SIZE", "C_NFIN", "C_GBELOW", "C_GNC", "C_BNC", "C_FLAGS", "C_BTOTAL",
                  "C_BBELOW", "K_ASPMIN", "K_GLO", "K_BLO", "F_VSHIFT", "F_MED"]
         self.lay = {k: int(v) for k, v in zip(names, lay)}
-        world = dist.get_world_size(self.group) if (self.sharded and dist.is_initialized()) else 1
+        world = (dist.get_world_size(self.group)
+                 if (self.sharded and dist.is_available() and dist.is_initialized()) else 1)
         self._world = world
         n_global = self._n_global
         # ~4 M sampled pixels over the whole raster (measured optimum of sample cost vs bracket width at 16384^2): one 4-pixel chunk out of every `stride`, jittered

@@ -55,6 +55,14 @@ def get_terrain_attribute(
     tensor; CUDA tensors are consumed in place and CUDA tensors are returned.  ``engine`` accepts the reference's
     values for signature compatibility but the CUDA engine always runs (there is no CPU fallback).
 
+    Output order: a list request returns ``outs[i]`` = attribute ``attribute[i]``.  The reference intends the same but
+    re-orders its category-grouped results with ``out[k] = grouped[attribute.index(grouped_names[k])]``
+    (terrain.py:648-656), i.e. it applies the permutation instead of its inverse: the two agree whenever that
+    permutation is an involution (any request inside one category, any two-category swap) and differ for 3-cycles across
+    the surface / windowed / frequency categories such as ``["roughness", "texture_shading", "slope"]``, where the
+    reference returns (texture_shading, slope, roughness).  This implementation deliberately keeps the requested order
+    (pinned by ``tests/test_terrain_gpu.py::test_three_cycle_request_keeps_requested_order``).
+
     :examples:
         >>> dem = np.repeat(np.arange(3), 3)[::-1].reshape(3, 3)
         >>> slope, aspect = get_terrain_attribute(dem, ["slope", "aspect"], resolution=1,
