@@ -374,7 +374,8 @@ def test_nk_bracketed_selection_equals_exhaustive(case: str) -> None:
     st = coreg._NKState(rt, tt, it)
     assert st.fast_eligible(72)
     n_fallback = 0
-    for dx, dy in ((0.0, 0.0), (0.37, -0.61), (-1.46, 2.58), (3.0, -2.0), (0.3712, -0.6093)):
+    # floor(dx) mod 4 = 0, 0, 2, 3, 1, 0: every column-shift instantiation of the full dh pass
+    for dx, dy in ((0.0, 0.0), (0.37, -0.61), (-1.46, 2.58), (3.0, -2.0), (1.3, 0.75), (0.3712, -0.6093)):
         res = st.iteration_fast(dx, dy, 72)
         if res is None:
             n_fallback += 1

@@ -38,7 +38,7 @@ constexpr int NT = 256;
 constexpr int MAXB = 96;
 constexpr int WSTAGE = 640;  // per-warp staging of compacted entries (a warp sees 2048 pixels of a 16384-wide row)
 // layout of the small device state arrays (also exported through xb_nkf_layout)
-enum { C_NFIN = 0, C_GBELOW = 1, C_GNC = 2, C_BNC = 3, C_FLAGS = 4, C_RFALL = 5, C_BTOTAL = 8, C_BBELOW = 8 + MAXB, C_SIZE = 8 + 2 * MAXB };
+enum { C_NFIN = 0, C_GBELOW = 1, C_GNC = 2, C_BNC = 3, C_FLAGS = 4, C_RFALL = 5, C_ROWQ_DH = 6, C_ROWQ_Y = 7, C_BTOTAL = 8, C_BBELOW = 8 + MAXB, C_SIZE = 8 + 2 * MAXB };
 enum { K_ASPMIN = 0, K_ASPMAX = 1, K_GLO = 2, K_GHI = 3, K_BLO = 4, K_BHI = 4 + MAXB, K_SIZE = 4 + 2 * MAXB };
 enum { F_VSHIFT = 0, F_ASPLO = 1, F_ASPHI = 2, F_CLO = 3, F_CHI = 4, F_M0 = 5, F_MED = 8, F_SIZE = 8 + MAXB };
 enum { FLAG_GMISS = 1, FLAG_GOVER = 2, FLAG_BMISS = 4, FLAG_BOVER = 8 };
@@ -224,6 +224,142 @@ nkf_dh_kernel(const DhArgs a, float* __restrict__ dh, unsigned* __restrict__ sam
     }
 }
 
+// The FULL pass again, specialised (ncu r02f on the kernel above: 58 thread-instructions per pixel of which 31 are 64-bit
+// index / bounds arithmetic repeated per 4-pixel chunk, and ten unaligned 4-byte loads per chunk that each touch a
+// 512-byte span of the warp): the column shift (c + j0) mod 4 is the same for every chunk of the raster, so the kernel
+// is instantiated per SHIFT and reads the two to-be-aligned rows as two ALIGNED float4 each, picking the five values of
+// the 2x2 stencils at compile-time positions; everything that only depends on the row is hoisted out of the column
+// loop, columns are 32-bit, and the aspect-range reduction only exists in the instantiation that needs it.  Chunks /
+// rows that touch the raster border take dh4().  Same FP64 expressions, term for term, as dh4 -> bit-identical dh.
+template <int SHIFT, bool HAS_ASPECT>
+__global__ void __launch_bounds__(NT)
+nkf_dh_full_kernel(const DhArgs a, float* __restrict__ dh, unsigned long long* __restrict__ cnt, unsigned* __restrict__ keys,
+                   unsigned* __restrict__ gcompact, unsigned long long gcap) {
+    __shared__ unsigned s_stage[NT / 32][WSTAGE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned wn = 0;  // staged entries of this warp (warp-uniform)
+    const unsigned glo = keys[K_GLO], ghi = keys[K_GHI];
+    unsigned lmin = 0xffffffffu, lmax = 0u;
+    unsigned nfin = 0, below = 0;  // per thread: < 2^32 pixels
+    const int cols = (int)a.cols;
+    const int j0 = (int)a.j0;  // |j0| < cols checked by the host
+    const double w00 = a.w00, w01 = a.w01, w10 = a.w10, w11 = a.w11;
+    // rows are handed out dynamically (one atomic per row and CTA): the grid is exactly the resident CTAs, so there is
+    // no second, partially filled wave (1184 CTAs on 740 resident slots ran at 80 % of the machine, ncu r02f)
+    __shared__ long long s_row;
+    for (;;) {
+        if (threadIdx.x == 0) s_row = (long long)atomicAdd(&cnt[C_ROWQ_DH], 1ull);
+        __syncthreads();
+        const long long r = s_row;
+        __syncthreads();
+        if (r >= a.rows) break;
+        const long long rr = r + a.i0 + a.tba_row0;
+        const bool row_fast = rr >= 0 && rr + 1 < a.tba_rows_total;
+        const float* __restrict__ t0 = a.tba + rr * a.tba_ld;
+        const float* __restrict__ t1 = t0 + a.tba_ld;
+        const float* __restrict__ ref_r = a.ref + r * a.ld;
+        const unsigned char* __restrict__ mk_r = a.sub_mask + r * a.cols;
+        const float* __restrict__ as_r = HAS_ASPECT ? a.aspect + r * a.cols : nullptr;
+        float* __restrict__ dh_r = dh + r * a.cols;
+        for (int c0 = 0; c0 < cols; c0 += 4 * NT) {
+            const int c = c0 + 4 * (int)threadIdx.x;
+            const bool in = c < cols;
+            float out[4] = {CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F};
+            float as[4] = {0.f, 0.f, 0.f, 0.f};
+            if (in) {
+                const int base = c + j0 - SHIFT;  // aligned (multiple of 4) start of the eight staged columns
+                if (row_fast && base >= 0 && base + 8 <= cols) {
+                    const uchar4 m4 = *reinterpret_cast<const uchar4*>(mk_r + c);
+                    const float4 r4 = *reinterpret_cast<const float4*>(ref_r + c);
+                    const float4 a0 = *reinterpret_cast<const float4*>(t0 + base);
+                    const float4 b0 = *reinterpret_cast<const float4*>(t0 + base + 4);
+                    const float4 a1 = *reinterpret_cast<const float4*>(t1 + base);
+                    const float4 b1 = *reinterpret_cast<const float4*>(t1 + base + 4);
+                    const float e0[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
+                    const float e1[8] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, b1.z, b1.w};
+                    const unsigned char mk[4] = {m4.x, m4.y, m4.z, m4.w};
+                    const float rf[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const double acc = w00 * (double)e0[SHIFT + k] + w01 * (double)e0[SHIFT + k + 1] +
+                                           w10 * (double)e1[SHIFT + k] + w11 * (double)e1[SHIFT + k + 1];
+                        out[k] = mk[k] ? (float)((double)rf[k] - acc) : CUDART_NAN_F;
+                    }
+                } else {
+                    dh4(a.ref, a.tba, a.sub_mask, r, c, a.cols, a.ld, a.tba_ld, a.tba_row0, a.tba_rows_total, a.i0, a.j0,
+                        w00, w01, w10, w11, out);
+                }
+                *reinterpret_cast<float4*>(dh_r + c) = make_float4(out[0], out[1], out[2], out[3]);
+                if constexpr (HAS_ASPECT) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(as_r + c);
+                    as[0] = a4.x, as[1] = a4.y, as[2] = a4.z, as[3] = a4.w;
+                }
+            }
+            unsigned key[4];
+            unsigned tmask = 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool fin = fabsf(out[u]) < CUDART_INF_F;
+                key[u] = ordered_key(out[u]);
+                if constexpr (HAS_ASPECT) {
+                    const unsigned ab = __float_as_uint(as[u]);  // aspect >= 0: bit pattern is monotonic
+                    lmin = fin ? min(lmin, ab) : lmin, lmax = fin ? max(lmax, ab) : lmax;
+                }
+                nfin += fin;
+                below += fin && key[u] < glo;
+                tmask |= (fin && key[u] >= glo && key[u] <= ghi) ? (1u << u) : 0u;
+            }
+            if (__any_sync(0xffffffffu, tmask != 0u)) {
+                // exclusive scan of the lanes' take counts
+                const unsigned nt = __popc(tmask);
+                unsigned incl = nt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                unsigned pos = wn + incl - nt;
+                wn += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (tmask & (1u << u)) {
+                        if (pos < WSTAGE) {
+                            s_stage[warp][pos] = key[u];
+                        } else {  // staging full (heavy ties): straight to the global buffer
+                            const unsigned long long gi = atomicAdd(&cnt[C_GNC], 1ull);
+                            if (gi < gcap) gcompact[gi] = key[u];
+                        }
+                        ++pos;
+                    }
+            }
+        }
+        // flush the row's staged keys of this warp
+        const unsigned n_st = min(wn, (unsigned)WSTAGE);
+        if (n_st) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&cnt[C_GNC], (unsigned long long)n_st);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            __syncwarp();
+            for (unsigned i = lane; i < n_st; i += 32)
+                if (base + i < gcap) gcompact[base + i] = s_stage[warp][i];
+            __syncwarp();
+        }
+        wn = 0;
+    }
+    if constexpr (HAS_ASPECT) {
+        lmin = __reduce_min_sync(0xffffffffu, lmin);
+        lmax = __reduce_max_sync(0xffffffffu, lmax);
+    }
+    const unsigned wfin = __reduce_add_sync(0xffffffffu, nfin), wbel = __reduce_add_sync(0xffffffffu, below);
+    // (a thread sees < 2^32 pixels, a warp's sum could only wrap beyond 2^32 pixels per warp: rows*cols/gridDim/8)
+    if (lane == 0) {
+        if (HAS_ASPECT && lmin != 0xffffffffu) atomicMin(&keys[K_ASPMIN], lmin);
+        if (HAS_ASPECT && wfin) atomicMax(&keys[K_ASPMAX], lmax);
+        if (wfin) atomicAdd(&cnt[C_NFIN], (unsigned long long)wfin);
+        if (wbel) atomicAdd(&cnt[C_GBELOW], (unsigned long long)wbel);
+    }
+}
+
 // aspect bin of binned_statistic(bins=n, range=None): see xbn::aspect_bin (xb_nuthkaab.cu) -- same code
 __device__ __forceinline__ int aspect_bin(float a, double lo, double hi, double step, double inv_step, int n_bins) {
     const double x = (double)a;
@@ -298,6 +434,7 @@ nkf_y_kernel(const float* __restrict__ dh, const float* __restrict__ slope_tan, 
     __shared__ unsigned s_stage[NT / 32][WSTAGE];
     __shared__ unsigned char s_stage_g[NT / 32][WSTAGE];
     __shared__ unsigned s_wn[NT / 32];  // staged entries per warp
+    __shared__ long long s_row;
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x < NT / 32) s_wn[threadIdx.x] = 0u;
     const unsigned wn_addr = (unsigned)__cvta_generic_to_shared(&s_wn[warp]);
@@ -316,7 +453,12 @@ nkf_y_kernel(const float* __restrict__ dh, const float* __restrict__ slope_tan, 
     double m0 = 0.0, m1 = 0.0, m2 = 0.0;
     auto rows_loop = [&](auto vf_tag) {
         constexpr bool VF = decltype(vf_tag)::value;
-        for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        for (;;) {  // dynamic row queue, see nkf_dh_full_kernel
+            if (threadIdx.x == 0) s_row = (long long)atomicAdd(&cnt[C_ROWQ_Y], 1ull);
+            __syncthreads();
+            const long long r = s_row;
+            __syncthreads();
+            if (r >= rows) break;
             const float* dh_r = dh + r * cols;
             const float* st_r = slope_tan + r * cols;
             const float* as_r = aspect + r * cols;
@@ -673,10 +815,17 @@ nk_prepare_vec4_kernel(const float* __restrict__ z, long long rows_buf, long lon
                        int bottom_is_border, long long row_begin, long long row_end, const float* __restrict__ tba,
                        long long tba_ld, const unsigned char* __restrict__ inlier, float* __restrict__ slope_tan,
                        float* __restrict__ aspect, unsigned char* __restrict__ sub_mask,
-                       unsigned long long* __restrict__ n_valid, unsigned* __restrict__ rec) {
+                       unsigned long long* __restrict__ n_valid, unsigned* __restrict__ rec,
+                       unsigned* __restrict__ row_queue) {
     unsigned lmin = 0xffffffffu, lmax = 0u, pmin = 0u, pmax = 0u;
     unsigned cnt = 0;
-    for (long long r = row_begin + blockIdx.x; r < row_end; r += gridDim.x) {
+    __shared__ long long s_row;
+    for (;;) {  // dynamic row queue: the grid is exactly the resident CTAs
+        if (threadIdx.x == 0) s_row = row_begin + (long long)atomicAdd(row_queue, 1u);
+        __syncthreads();
+        const long long r = s_row;
+        __syncthreads();
+        if (r >= row_end) break;
         const float* zr = z + r * ld;
         const bool top = (r == 0) && top_is_border;
         const bool bot = (r == rows_buf - 1) && bottom_is_border;
@@ -845,6 +994,16 @@ __global__ void nkf_finalize_kernel(unsigned long long* cnt, double* f64, unsign
     f64[F_CHI] = f64[F_ASPHI];
 }
 
+// exactly the CTAs that are resident at once (for kernels that pull their rows from a queue)
+template <class K>
+static int grid_resident(K kernel, int threads, long long n_units) {
+    int sms = 0, occ = 0;
+    if (xb_num_sms(&sms)) sms = 148;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, 0) != cudaSuccess || occ < 1) occ = 1;
+    const long long cap = (long long)sms * occ;
+    return (int)(n_units < cap ? (n_units < 1 ? 1 : n_units) : cap);
+}
+
 static int grid_rows(long long n_rows, int per_sm) {
     int sms = 0;
     if (xb_num_sms(&sms)) sms = 148;
@@ -882,13 +1041,15 @@ int xb_nk_prepare(const float* ref_dev, int64_t rows_buf, int64_t cols, int64_t 
                         reinterpret_cast<uintptr_t>(slope_tan_dev) | reinterpret_cast<uintptr_t>(aspect_dev)) % 16 == 0) &&
                       ((reinterpret_cast<uintptr_t>(sub_mask_dev) | reinterpret_cast<uintptr_t>(inlier_dev)) % 4 == 0);
     if (vec4) {
-        const int grid = xbf::grid_rows(rows, 8);
+        const int grid = xbf::grid_resident(xbf::nk_prepare_vec4_kernel, xbf::NT, rows);
         const int n_rec = grid * (xbf::NT / 32);
-        unsigned* rec = nullptr;
-        XB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&rec), (size_t)n_rec * 4 * sizeof(unsigned), st));
+        unsigned* rec = nullptr;  // per-warp records + the row queue counter
+        XB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&rec), ((size_t)n_rec * 4 + 1) * sizeof(unsigned), st));
+        XB_CUDA_CHECK(cudaMemsetAsync(rec + (size_t)n_rec * 4, 0, sizeof(unsigned), st));
         xbf::nk_prepare_vec4_kernel<<<grid, xbf::NT, 0, st>>>(ref_dev, rows_buf, cols, ld, top_is_border, bottom_is_border,
                                                               row_begin, row_end, tba_dev, tba_ld, inlier_dev,
-                                                              slope_tan_dev, aspect_dev, sub_mask_dev, n_valid_dev, rec);
+                                                              slope_tan_dev, aspect_dev, sub_mask_dev, n_valid_dev, rec,
+                                                              rec + (size_t)n_rec * 4);
         xbf::nk_candidates_kernel<<<1, 1024, 0, st>>>(rec, n_rec, range_cand_dev);
         XB_CUDA_CHECK(cudaGetLastError());
         XB_CUDA_CHECK(cudaFreeAsync(rec, st));
@@ -957,10 +1118,24 @@ int xb_nkf_dh(int sample, const float* ref_dev, const float* tba_dev, const uint
     const long long n_schunks = (rows * (cols / 4) + stride - 1) / stride;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (sample)
-        xbf::nkf_dh_kernel<true><<<xbf::grid_rows((n_schunks + xbf::NT - 1) / xbf::NT, 8), xbf::NT, 0, st>>>(
+        xbf::nkf_dh_kernel<true><<<xbf::grid_resident(xbf::nkf_dh_kernel<true>, xbf::NT, (n_schunks + xbf::NT - 1) / xbf::NT), xbf::NT, 0, st>>>(
             a, nullptr, sample_dev, stride, seed, n_schunks, cnt_dev, keys_dev, nullptr, 0);
-    else
-        xbf::nkf_dh_kernel<false><<<xbf::grid_rows(rows, 8), xbf::NT, 0, st>>>(a, dh_dev, nullptr, stride, seed,
+    else if (llabs(a.j0) < cols && cols < (1ll << 30) && tba_ld % 4 == 0 && reinterpret_cast<uintptr_t>(tba_dev) % 16 == 0 &&
+             rows * cols / 8 < (1ll << 32)) {
+        const int shift = (int)(((a.j0 % 4) + 4) % 4);
+#define XB_DH_CASE(S)                                                                                                 \
+    case S:                                                                                                           \
+        if (aspect_dev)                                                                                               \
+            xbf::nkf_dh_full_kernel<S, true><<<xbf::grid_resident(xbf::nkf_dh_full_kernel<S, true>, xbf::NT, rows),    \
+                                               xbf::NT, 0, st>>>(a, dh_dev, cnt_dev, keys_dev, gcompact_dev, gcap);    \
+        else                                                                                                          \
+            xbf::nkf_dh_full_kernel<S, false><<<xbf::grid_resident(xbf::nkf_dh_full_kernel<S, false>, xbf::NT, rows),  \
+                                                xbf::NT, 0, st>>>(a, dh_dev, cnt_dev, keys_dev, gcompact_dev, gcap);   \
+        break;
+        switch (shift) { XB_DH_CASE(0) XB_DH_CASE(1) XB_DH_CASE(2) XB_DH_CASE(3) }
+#undef XB_DH_CASE
+    } else
+        xbf::nkf_dh_kernel<false><<<xbf::grid_resident(xbf::nkf_dh_kernel<false>, xbf::NT, rows), xbf::NT, 0, st>>>(a, dh_dev, nullptr, stride, seed,
                                                                                n_schunks, cnt_dev, keys_dev, gcompact_dev,
                                                                                gcap);
     XB_CUDA_CHECK(cudaGetLastError());
@@ -989,11 +1164,11 @@ int xb_nkf_y(int sample, const float* dh_dev, const float* slope_tan_dev, const 
     const long long n_schunks = (rows * (cols / 4) + stride - 1) / stride;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (sample)
-        xbf::nkf_y_kernel<true><<<xbf::grid_rows((n_schunks + xbf::NT - 1) / xbf::NT, 8), xbf::NT, 0, st>>>(
+        xbf::nkf_y_kernel<true><<<xbf::grid_resident(xbf::nkf_y_kernel<true>, xbf::NT, (n_schunks + xbf::NT - 1) / xbf::NT), xbf::NT, 0, st>>>(
             dh_dev, slope_tan_dev, aspect_dev, bin_cache_dev, rows, cols, n_bins, skey_dev, sgrp_dev, stride, seed,
             n_schunks, cnt_dev, keys_dev, f64_dev, nullptr, nullptr, 0);
     else
-        xbf::nkf_y_kernel<false><<<xbf::grid_rows(rows, 8), xbf::NT, 0, st>>>(
+        xbf::nkf_y_kernel<false><<<xbf::grid_resident(xbf::nkf_y_kernel<false>, xbf::NT, rows), xbf::NT, 0, st>>>(
             dh_dev, slope_tan_dev, aspect_dev, bin_cache_dev, rows, cols, n_bins, nullptr, nullptr, stride, seed,
             n_schunks, cnt_dev, keys_dev, f64_dev, bkey_dev, bgrp_dev, bcap);
     XB_CUDA_CHECK(cudaGetLastError());
