@@ -655,6 +655,30 @@ def main() -> None:
         e2e["pinned"] = {"value": pixels_total * args.e2e_steps / dtp / 1e6, "unit": "Mpixel/s",
                          "ms_per_step": dtp / args.e2e_steps * 1e3,
                          "call": "xb_terrain_fused_host_rows (C ABI), page-locked DEM in, page-locked planes out"}
+        # what the platform gives: plain cudaMemcpyAsync device -> page-locked host, every rank at once (no kernel, no
+        # staging, no API): the aggregate is a property of the host (root complexes / memory), not of this code
+        try:
+            p_src = view if view.is_contiguous() else view.contiguous()
+            p_dst = torch.from_numpy(h_out[0])
+            n_el = min(p_src.numel(), p_dst.numel())
+            p_src, p_dst = p_src.reshape(-1)[:n_el], p_dst.reshape(-1)[:n_el]
+            p_dst.copy_(p_src, non_blocking=True)
+            torch.cuda.synchronize()
+            ctx.barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                p_dst.copy_(p_src, non_blocking=True)
+            torch.cuda.synchronize()
+            dtl = ctx.max_over_ranks(time.perf_counter() - t0)
+            per_gpu = 3 * n_el * 4 / dtl / 1e9
+            e2e["d2h_link_probe"] = {
+                "gbs_per_gpu": per_gpu, "gbs_total": per_gpu * world,
+                "what": "plain cudaMemcpyAsync device -> page-locked host, all ranks at once, 3 x %.1f GB per rank"
+                        % (n_el * 4 / 1e9),
+                "e2e_pinned_d2h_gbs_total": d2h / (dtp / args.e2e_steps) / 1e9,
+            }
+        except Exception as ex:  # noqa: BLE001 -- the probe must never cost the bench line
+            e2e["d2h_link_probe"] = {"error": f"{type(ex).__name__}: {ex}"}
         del host_in, h_in, h_out, dem_np
     del buf, core
     torch.cuda.empty_cache()
