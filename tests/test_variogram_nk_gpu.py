@@ -246,6 +246,53 @@ def test_nk_aux_bit_exact() -> None:
     assert np.nanmax(np.abs(asp - g["aspect"])) <= 4 * np.spacing(np.float32(6.3))  # atan2f: a few ulp
 
 
+@pytest.mark.parametrize("shape", [(257, 403), (256, 512)])
+def test_nk_prepare_mask_count_and_range_candidates(shape) -> None:
+    """xb_nk_prepare (one pass: aux variables + validity mask + count + aspect-range candidates), scalar kernel (odd
+    width) and 4-pixels-per-thread kernel: slope_tan / aspect identical to xb_nk_aux, mask == inlier & finite(ref, tba,
+    slope_tan, aspect) (base.py:653-661), the count, and candidates that really attain the min / max valid aspect."""
+    import ctypes
+
+    import torch
+
+    from oracle import synth
+    from xdem_b200 import _lib, coreg
+
+    ref, tba = synth.nk_pair(shape, shift_px=(0.3, -0.2), dz=1.0, noise=0.05)
+    ref, tba = ref.astype(np.float32), tba.astype(np.float32)
+    ref[10:14, 20:40] = np.nan
+    tba[100:120, 5:9] = np.nan
+    ref[200:210, 300:330] = 7.0  # flat patch: slope_tan == 0 -> NaN (affine.py:578-579)
+    inl = np.random.default_rng(3).random(shape) < 0.9
+    rt, tt = torch.from_numpy(ref).cuda(), torch.from_numpy(tba).cuda()
+    for mask in (None, torch.from_numpy(inl).cuda()):
+        st = coreg._NKState(rt, tt, mask)
+        L = _lib.lib()
+        st_ref = torch.empty_like(rt)
+        asp_ref = torch.empty_like(rt)
+        _lib.check(L.xb_nk_aux(rt.data_ptr(), shape[0], shape[1], rt.stride(0), 1, 1, 0, shape[0], st_ref.data_ptr(),
+                               asp_ref.data_ptr(), shape[1], ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        assert torch.equal(st.slope_tan.view(torch.int32), st_ref.view(torch.int32))
+        assert torch.equal(st.aspect.view(torch.int32), asp_ref.view(torch.int32))
+        valid = torch.isfinite(rt) & torch.isfinite(tt) & torch.isfinite(st_ref) & torch.isfinite(asp_ref)
+        if mask is not None:
+            valid &= mask
+        assert torch.equal(st.sub_mask.bool(), valid) and torch.equal(st.valid, valid)
+        assert st.n_valid() == int(valid.sum().item())
+        rc = st.range_cand.cpu().numpy().view(np.uint32)
+        asp = st.aspect.cpu().numpy()
+        v = valid.cpu().numpy()
+        assert rc[0:1].view(np.float32)[0] == asp[v].min() and rc[1:2].view(np.float32)[0] == asp[v].max()
+        assert 1 <= rc[2] <= 64 and 1 <= rc[3] <= 64
+        for k in range(int(rc[2])):
+            i = int(rc[4 + k])
+            assert v.flat[i] and asp.flat[i] == asp[v].min()
+        for k in range(int(rc[3])):
+            i = int(rc[4 + 64 + k])
+            assert v.flat[i] and asp.flat[i] == asp[v].max()
+
+
 def test_nk_step_pieces_vs_oracle() -> None:
     """dh, its exact median, the per-bin medians / counts and p0 of one iteration against the oracle."""
     import torch
