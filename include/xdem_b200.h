@@ -255,6 +255,15 @@ int xb_nk_aux(const float* ref_dev, int64_t rows_buf, int64_t cols, int64_t ld, 
               int bottom_is_border, int64_t row_begin, int64_t row_end, float* slope_tan_dev, float* aspect_dev,
               int64_t out_ld, void* stream);
 
+/* dh at a list of pixels (row-major linear indices idx_dev[n_pts] into the rows x cols raster): the reference's default
+ * fit works on a random subsample of 5e5 valid points (affine.py:2405, base.py:576-621) -- the pass then touches only
+ * those points instead of streaming the rasters.  dh_dev[i] belongs to point i; aspect_pts_dev is the aspect gathered at
+ * the points; asp_minmax / n_finite as in xb_nk_dh. */
+int xb_nk_dh_points(const float* ref_dev, const float* tba_dev, const int64_t* idx_dev, int64_t n_pts,
+                    const float* aspect_pts_dev, int64_t rows, int64_t cols, int64_t ld, int64_t tba_ld, int64_t tba_row0,
+                    int64_t tba_rows_total, double dx_px, double dy_px, float* dh_dev, uint32_t* asp_minmax_dev,
+                    unsigned long long* n_finite_dev, void* stream);
+
 /* xb_nk_aux fused with the validity mask of the fit (`_preprocess_rst_pts_subsample`, base.py:653-661):
  * sub_mask = inlier (NULL: all) & finite(ref, tba, slope_tan, aspect), n_valid_dev[0] = its population, and
  * range_cand_dev (uint32[4 + 2*64]) = {aspect min bits, max bits over the valid pixels, n_min, n_max, up to 64 pixel
@@ -371,6 +380,16 @@ int xb_nkf_iteration(const float* ref_dev, const float* tba_dev, const uint8_t* 
                      unsigned long long* cnt_dev, uint32_t* keys_dev, double* f64_dev, uint32_t* hist_dev,
                      uint32_t* prefix_dev, unsigned long long* below_dev, long long* rank_dev,
                      const uint32_t* range_cand_dev, void* stream);
+
+/* One whole iteration of a point-list fit (see xb_nk_dh_points): exact median of dh, aspect range, exact per-bin medians
+ * / counts / moments of y = (dh - median)/slope_tan at the points, all on the device; results in the same cnt / f64
+ * block as xb_nkf_iteration.  key_dev / grp_dev: scratch of n_pts entries. */
+int xb_nkf_iteration_points(const float* ref_dev, const float* tba_dev, const int64_t* idx_dev, int64_t n_pts,
+                            const float* slope_tan_pts_dev, const float* aspect_pts_dev, int64_t rows, int64_t cols,
+                            int64_t ld, int64_t tba_ld, int64_t tba_row0, int64_t tba_rows_total, double dx_px,
+                            double dy_px, int n_bins, float* dh_pts_dev, uint32_t* key_dev, uint8_t* grp_dev,
+                            unsigned long long* cnt_dev, uint32_t* keys_dev, double* f64_dev, uint32_t* hist_dev,
+                            uint32_t* prefix_dev, unsigned long long* below_dev, long long* rank_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -453,6 +453,42 @@ def test_nk_bracketed_selection_equals_exhaustive(case: str) -> None:
     assert fast[1] == slow[1] and np.allclose(fast[0], slow[0], rtol=1e-5, atol=1e-7), (fast, slow)
 
 
+def test_nk_point_list_iteration_equals_exhaustive() -> None:
+    """Point-list fits (the reference's default: a random subsample of points): the all-device iteration
+    (xb_nkf_iteration_points) returns exactly what the exhaustive host-driven radix select returns on the same points --
+    n, aspect range, median of dh, per-bin medians and counts -- and the picked points are valid, unique and as many as
+    asked for; the whole fit recovers the synthetic shift."""
+    import torch
+
+    from oracle import synth
+    from xdem_b200 import coreg
+
+    ref, tba = synth.nk_pair((1200, 1604), shift_px=(0.37, -0.61), dz=1.5, noise=0.05)
+    tba[100:300, 300:700] = np.nan
+    rt, tt = torch.from_numpy(ref).cuda(), torch.from_numpy(tba).cuda()
+    st = coreg._NKState(rt, tt, None)
+    idx = coreg._pick_valid_points(st, 200_000, st.n_valid(), 7)
+    assert idx.numel() == 200_000 and torch.unique(idx).numel() == 200_000
+    assert bool(st.sub_mask.view(-1)[idx].all())
+    assert torch.equal(idx, coreg._pick_valid_points(st, 200_000, st.n_valid(), 7))  # deterministic for an int seed
+    st.set_points(idx)
+    for dx, dy in ((0.0, 0.0), (0.37, -0.61), (-1.46, 2.58), (25.0, -13.5)):
+        res = st.iteration_points(dx, dy, 72)
+        assert res is not None
+        lo, hi, n_fin = st.compute_dh(dx, dy)
+        med, cnt, _ = st.select_medians(0, 0.0, 0.0, 1.0, 1)
+        assert res["n_fin"] == n_fin == cnt[0] and res["lo"] == lo and res["hi"] == hi
+        assert res["vshift"] == float(med[0])
+        med_b, cnt_b, mom = st.select_medians(1, float(med[0]), lo, hi, 72, want_moments=True)
+        assert np.array_equal(res["counts"], cnt_b)
+        assert np.array_equal(res["median"], med_b, equal_nan=True)
+        assert res["moments"][0] == mom[0] and np.allclose(res["moments"], mom, rtol=1e-9)
+    (e, n, vz), used = coreg.nuth_kaab(rt, tt, transform=(5.0, 0, 0, 0, -5.0, 0), tolerance=0.0, max_iterations=6,
+                                       params_random={"subsample": 3e5, "random_state": 1})
+    assert used == 300_000
+    assert abs(e / 5 + 0.37) < 2e-2 and abs(n / 5 + 0.61) < 2e-2 and abs(vz + 1.5) < 2e-2, (e, n, vz)
+
+
 def test_nk_apply_translation() -> None:
     """`apply`: regrid of the shifted DEM on the input grid == map_coordinates restatement; after
     applying the fitted shift the residual dh median is ~0 and a second fit finds (almost) no shift."""

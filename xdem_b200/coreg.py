@@ -128,6 +128,18 @@ class _NKState:
         self.sub_mask = mask_u8
         self.range_cand = None
 
+    def set_points(self, idx: torch.Tensor) -> None:
+        """Restrict the fit to a list of valid pixels (row-major linear indices, int64) -- the reference's default
+        (a random subsample of 5e5 points, affine.py:2405): dh is then evaluated at those points only
+        (xb_nk_dh_points) and every later pass works on compact arrays of that length instead of the rasters."""
+        self.pt_idx = idx.to(torch.int64).contiguous()
+        self.slope_tan = self.slope_tan.view(-1)[self.pt_idx].contiguous()
+        self.aspect = self.aspect.view(-1)[self.pt_idx].contiguous()
+        self.n = int(self.pt_idx.numel())
+        self.dh = torch.empty(self.n, dtype=torch.float32, device=self.dev)
+        self.range_cand = None
+        self._keys = None
+
     # ------------------------------------------------------------------ device passes
     def compute_dh(self, dx_px: float, dy_px: float) -> tuple[float, float, int]:
         import torch.distributed as dist
@@ -141,10 +153,18 @@ class _NKState:
         mm = _u32_tensor(np.array([0xFFFFFFFF, 0], dtype=np.uint32), self.dev)
         cnt = torch.zeros(1, dtype=torch.int64, device=self.dev)
         with torch.cuda.device(self.dev):
-            _lib.check(self.L.xb_nk_dh(self.ref.data_ptr(), self.tba_buf.data_ptr(), self.sub_mask.data_ptr(),
-                                       self.aspect.data_ptr(), self.rows, self.cols, self.ref.stride(0),
-                                       self.tba_buf.stride(0), self.tba_row0, self.tba_buf.shape[0], float(dx_px),
-                                       float(dy_px), self.dh.data_ptr(), mm.data_ptr(), cnt.data_ptr(), self.stream))
+            if getattr(self, "pt_idx", None) is not None:
+                _lib.check(self.L.xb_nk_dh_points(self.ref.data_ptr(), self.tba_buf.data_ptr(), self.pt_idx.data_ptr(),
+                                                  self.n, self.aspect.data_ptr(), self.rows, self.cols,
+                                                  self.ref.stride(0), self.tba_buf.stride(0), self.tba_row0,
+                                                  self.tba_buf.shape[0], float(dx_px), float(dy_px), self.dh.data_ptr(),
+                                                  mm.data_ptr(), cnt.data_ptr(), self.stream))
+            else:
+                _lib.check(self.L.xb_nk_dh(self.ref.data_ptr(), self.tba_buf.data_ptr(), self.sub_mask.data_ptr(),
+                                           self.aspect.data_ptr(), self.rows, self.cols, self.ref.stride(0),
+                                           self.tba_buf.stride(0), self.tba_row0, self.tba_buf.shape[0], float(dx_px),
+                                           float(dy_px), self.dh.data_ptr(), mm.data_ptr(), cnt.data_ptr(),
+                                           self.stream))
         mm64 = mm.to(torch.int64) & 0xFFFFFFFF
         if self.sharded and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             lo_t, hi_t = mm64[0:1].clone(), mm64[1:2].clone()
@@ -189,6 +209,8 @@ class _NKState:
         import torch.distributed as dist
 
         if not NK_FAST or n_bins > 96 or self.cols % 4 or self.ref.stride(0) % 4 or self.tba_buf.stride(0) % 4:
+            return False
+        if getattr(self, "pt_idx", None) is not None:  # point-list fits never stream the rasters
             return False
         n_global = self.n
         if self.sharded and dist.is_available() and dist.is_initialized():
@@ -377,6 +399,41 @@ class _NKState:
             f_h = f64.cpu().numpy()
         return self._fast_result(cnt_h, f_h, n_bins)
 
+    def iteration_points(self, dx_px: float, dy_px: float, n_bins: int) -> dict[str, Any] | None:
+        """One iteration of a point-list fit (``set_points``) entirely on the device (xb_nkf_iteration_points): exact
+        medians by radix select over ALL points, ranks picked on the device, one host read.  Same result dictionary as
+        ``iteration_fast``."""
+        L, dev = self.L, self.dev
+        if getattr(self, "_points_ready", None) is None:
+            lay = (ctypes.c_int32 * 16)()
+            _lib.check(L.xb_nkf_layout(lay))
+            names = ["MAXB", "C_SIZE", "K_SIZE", "F_SIZE", "C_NFIN", "C_GBELOW", "C_GNC", "C_BNC", "C_FLAGS", "C_BTOTAL",
+                     "C_BBELOW", "K_ASPMIN", "K_GLO", "K_BLO", "F_VSHIFT", "F_MED"]
+            self.lay = {k: int(v) for k, v in zip(names, lay)}
+            i32, u8, i64, f64 = torch.int32, torch.uint8, torch.int64, torch.float64
+            maxb = self.lay["MAXB"]
+            self.f_cnt = torch.zeros(self.lay["C_SIZE"], dtype=i64, device=dev)
+            self.f_keys = torch.zeros(self.lay["K_SIZE"], dtype=i32, device=dev)
+            self.f_f64 = torch.full((self.lay["F_SIZE"],), float("nan"), dtype=f64, device=dev)
+            self.f_hist = torch.zeros(2 * maxb * 256, dtype=i32, device=dev)
+            self.f_prefix = torch.zeros(2 * maxb, dtype=i32, device=dev)
+            self.f_below = torch.zeros(2 * maxb, dtype=i64, device=dev)
+            self.f_rank = torch.zeros(2 * maxb, dtype=i64, device=dev)
+            self.p_key = torch.empty(self.n, dtype=i32, device=dev)
+            self.p_grp = torch.empty(self.n, dtype=u8, device=dev)
+            self._points_ready = True
+        with torch.cuda.device(dev):
+            _lib.check(L.xb_nkf_iteration_points(
+                self.ref.data_ptr(), self.tba_buf.data_ptr(), self.pt_idx.data_ptr(), self.n, self.slope_tan.data_ptr(),
+                self.aspect.data_ptr(), self.rows, self.cols, self.ref.stride(0), self.tba_buf.stride(0), self.tba_row0,
+                self.tba_buf.shape[0], float(dx_px), float(dy_px), n_bins, self.dh.data_ptr(), self.p_key.data_ptr(),
+                self.p_grp.data_ptr(), self.f_cnt.data_ptr(), self.f_keys.data_ptr(), self.f_f64.data_ptr(),
+                self.f_hist.data_ptr(), self.f_prefix.data_ptr(), self.f_below.data_ptr(), self.f_rank.data_ptr(),
+                self.stream))
+            cnt_h = self.f_cnt.cpu().numpy()  # the iteration's only host synchronisation
+            f_h = self.f_f64.cpu().numpy()
+        return self._fast_result(cnt_h, f_h, n_bins)
+
     def _fast_result(self, cnt_h: np.ndarray, f_h: np.ndarray, n_bins: int) -> dict[str, Any] | None:
         lay = self.lay
         self.fast_last_flags = int(cnt_h[lay["C_FLAGS"]])
@@ -515,10 +572,11 @@ def _nuth_kaab_iteration_step_gpu(coords_offsets: tuple[float, float, float], st
     """affine.py:477-536."""
     dx_px = coords_offsets[0] / a_e[0]
     dy_px = coords_offsets[1] / a_e[1]
+    points = getattr(state, "pt_idx", None) is not None and NK_FAST and int(bin_sizes) <= 96 and not state.sharded
     if getattr(state, "use_fast", None) is None:
-        state.use_fast = state.fast_eligible(int(bin_sizes))
+        state.use_fast = points or state.fast_eligible(int(bin_sizes))
     if state.use_fast:
-        res = state.iteration_fast(dx_px, dy_px, int(bin_sizes))
+        res = (state.iteration_points if points else state.iteration_fast)(dx_px, dy_px, int(bin_sizes))
         if res is not None:
             if res["n_fin"] == 0:
                 raise ValueError(
@@ -593,16 +651,32 @@ def nuth_kaab(ref_elev: Any, tba_elev: Any, inlier_mask: Any = None, transform: 
     if sub is not None and sub != 1.0:
         want = int(sub) if sub > 1 else int(sub * n_valid)
         if want < n_valid:
-            rng = np.random.default_rng(pr["random_state"])
-            idx_valid = torch.nonzero(state.valid.flatten()).flatten()
-            pick = torch.from_numpy(rng.choice(n_valid, size=want, replace=False)).to(state.dev)
-            m = torch.zeros(state.n, dtype=torch.uint8, device=state.dev)
-            m[idx_valid[pick]] = 1
-            state.set_subsample(m.view(state.rows, state.cols).contiguous())
+            state.set_points(_pick_valid_points(state, want, n_valid, pr["random_state"]))
             n_valid = want
     offsets = _iterate_nuth_kaab(state, transform, int(pf["bin_sizes"]), pf["fit_optimizer"], tolerance,
                                  max_iterations)
     return offsets, n_valid
+
+
+def _pick_valid_points(state: _NKState, want: int, n_valid: int, random_state: Any) -> torch.Tensor:
+    """A uniformly random subset of ``want`` valid pixels (sorted linear indices), drawn on the device.  Sparse draws --
+    the default 5e5 of a large raster -- use rejection sampling (uniform positions, duplicates removed, invalid ones
+    dropped, a random ``want`` of the survivors kept), so nothing of the raster's size is materialised; dense draws fall
+    back to a permutation of all valid positions.  Deterministic for an integer ``random_state``."""
+    dev, n = state.dev, state.rows * state.cols
+    seed = int(np.random.default_rng(random_state).integers(0, 2**62))
+    g = torch.Generator(device=dev).manual_seed(seed)
+    mask_flat = state.sub_mask.view(-1)
+    k = int(want * (n / max(n_valid, 1)) * 1.1) + 4096
+    if k < n // 8:
+        cand = torch.unique(torch.randint(0, n, (k,), generator=g, device=dev))
+        cand = cand[mask_flat[cand] != 0]
+        if cand.numel() >= want:
+            keep = torch.randperm(cand.numel(), generator=g, device=dev)[:want]
+            return cand[keep].sort().values
+    idx_valid = torch.nonzero(mask_flat).flatten()
+    keep = torch.randperm(idx_valid.numel(), generator=g, device=dev)[:want]
+    return idx_valid[keep].sort().values
 
 
 def make_reference_hook(reference_nuth_kaab: Callable[..., Any]) -> Callable[..., Any]:

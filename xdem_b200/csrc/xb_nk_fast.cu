@@ -568,6 +568,50 @@ nkf_y_kernel(const float* __restrict__ dh, const float* __restrict__ slope_tan, 
     }
 }
 
+// Point-list fits (the reference's default subsample of 5e5 points): the arrays are small, so there is nothing to
+// bracket -- the selection runs on ALL keys, entirely on the device.
+__global__ void __launch_bounds__(NT) nkf_keys_points_kernel(const float* __restrict__ dh, long long n,
+                                                              unsigned* __restrict__ key) {
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+        const float v = dh[i];
+        key[i] = isfinite(v) ? ordered_key(v) : 0u;
+    }
+}
+// (key of y, aspect bin) of every point + count / sum / sum of squares of y
+__global__ void __launch_bounds__(NT)
+nkf_y_points_kernel(const float* __restrict__ dh, const float* __restrict__ slope_tan, const float* __restrict__ aspect,
+                    long long n, int n_bins, unsigned* __restrict__ skey, unsigned char* __restrict__ sgrp,
+                    double* __restrict__ f64) {
+    const double vshift = f64[F_VSHIFT], lo = f64[F_ASPLO], hi = f64[F_ASPHI];
+    const double step = (hi - lo) / (double)n_bins;
+    const double inv_step = step > 0.0 ? 1.0 / step : 0.0;
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+        const float a = aspect[i];
+        unsigned kk = 0u;
+        unsigned char g = 255;
+        float yf = 0.f;
+        if (isfinite(a) && y_key(dh[i], slope_tan[i], vshift, kk, yf)) {
+            g = (unsigned char)aspect_bin(a, lo, hi, step, inv_step, n_bins);
+            m0 += 1.0, m1 += (double)yf, m2 += (double)yf * (double)yf;
+        } else {
+            kk = 0u;
+        }
+        skey[i] = kk, sgrp[i] = g;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m0 += __shfl_xor_sync(0xffffffffu, m0, o);
+        m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+        m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+    }
+    if ((threadIdx.x & 31) == 0 && m0 > 0.0) {
+        atomicAdd(&f64[F_M0], m0);
+        atomicAdd(&f64[F_M0 + 1], m1);
+        atomicAdd(&f64[F_M0 + 2], m2);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Radix select on a small buffer, two order statistics per group, ranks chosen on the device.
 // ---------------------------------------------------------------------------------------------------------------
@@ -1278,6 +1322,46 @@ int xb_nkf_iteration(const float* ref_dev, const float* tba_dev, const uint8_t* 
                        prefix_dev, below_dev, rank_dev, stream);
     if (rc) return rc;
     return xb_nkf_finalize(cnt_dev, f64_dev, gcap, bcap, stream);
+}
+
+/* One whole iteration of a point-list fit (xdem_b200.coreg._NKState.set_points): dh at the points, its exact median, the
+ * aspect range, (key, bin) of y at every point with the moments, the exact per-bin medians and counts -- all on the
+ * device, same result block as xb_nkf_iteration (cnt / f64), one host read at the end. */
+int xb_nkf_iteration_points(const float* ref_dev, const float* tba_dev, const int64_t* idx_dev, int64_t n_pts,
+                            const float* slope_tan_pts_dev, const float* aspect_pts_dev, int64_t rows, int64_t cols,
+                            int64_t ld, int64_t tba_ld, int64_t tba_row0, int64_t tba_rows_total, double dx_px,
+                            double dy_px, int n_bins, float* dh_pts_dev, uint32_t* key_dev, uint8_t* grp_dev,
+                            unsigned long long* cnt_dev, uint32_t* keys_dev, double* f64_dev, uint32_t* hist_dev,
+                            uint32_t* prefix_dev, unsigned long long* below_dev, long long* rank_dev, void* stream) {
+    using namespace xbf;
+    if (!slope_tan_pts_dev || !key_dev || !grp_dev || n_pts <= 0 || n_bins < 1 || n_bins > MAXB) {
+        xb_set_error("bad arguments to xb_nkf_iteration_points (1 <= n_bins <= %d)", MAXB);
+        return XB_ERR_INVALID;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = xb_nkf_reset(cnt_dev, keys_dev, f64_dev, hist_dev, stream);
+    if (rc) return rc;
+    rc = xb_nk_dh_points(ref_dev, tba_dev, idx_dev, n_pts, aspect_pts_dev, rows, cols, ld, tba_ld, tba_row0, tba_rows_total,
+                         dx_px, dy_px, dh_pts_dev, keys_dev + K_ASPMIN, cnt_dev + C_NFIN, stream);
+    if (rc) return rc;
+    const int grid = grid_rows((n_pts + NT - 1) / NT, 8);
+    nkf_keys_points_kernel<<<grid, NT, 0, st>>>(dh_pts_dev, n_pts, key_dev);
+    XB_CUDA_CHECK(cudaGetLastError());
+    // mode 2 with zero "above" / "below" counters: the population is exactly the buffer
+    rc = xb_nkf_select(key_dev, nullptr, 1, n_pts, nullptr, 1, 1, 2, cnt_dev + C_GNC, cnt_dev + C_GBELOW, nullptr, nullptr,
+                       f64_dev + F_VSHIFT, cnt_dev + C_FLAGS, FLAG_GMISS, hist_dev, prefix_dev, below_dev, rank_dev, stream);
+    if (rc) return rc;
+    rc = xb_nkf_range(keys_dev, f64_dev, stream);
+    if (rc) return rc;
+    nkf_y_points_kernel<<<grid, NT, 0, st>>>(dh_pts_dev, slope_tan_pts_dev, aspect_pts_dev, n_pts, n_bins, key_dev, grp_dev,
+                                             f64_dev);
+    XB_CUDA_CHECK(cudaGetLastError());
+    xb_count_launch(2);
+    rc = xb_nkf_select(key_dev, grp_dev, 1, n_pts, nullptr, 1, n_bins, 2, cnt_dev + C_BTOTAL, cnt_dev + C_BBELOW, nullptr,
+                       nullptr, f64_dev + F_MED, cnt_dev + C_FLAGS, FLAG_BMISS, hist_dev, prefix_dev, below_dev, rank_dev,
+                       stream);
+    if (rc) return rc;
+    return xb_nkf_finalize(cnt_dev, f64_dev, ~0ull, ~0ull, stream);
 }
 
 #pragma GCC visibility pop

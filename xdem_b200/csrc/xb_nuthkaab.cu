@@ -118,6 +118,53 @@ nk_dh_kernel(const float* __restrict__ ref, const float* __restrict__ tba, const
     }
 }
 
+// dh at a LIST of pixels (the reference's default: a random subsample of 5e5 valid points, affine.py:2405,
+// base.py:576-621): one thread per point, same FP64 expressions as nk_dh_kernel, outputs compact (dh[i] belongs to
+// point i).  aspect_pts is the aspect gathered at the points (compact, same order).
+__global__ void __launch_bounds__(NT)
+nk_dh_points_kernel(const float* __restrict__ ref, const float* __restrict__ tba, const long long* __restrict__ idx,
+                    long long n_pts, const float* __restrict__ aspect_pts, long long cols, long long ld, long long tba_ld,
+                    long long tba_row0, long long tba_rows_total, long long i0, long long j0, double w00, double w01,
+                    double w10, double w11, float* __restrict__ dh, unsigned* __restrict__ asp_minmax,
+                    unsigned long long* __restrict__ n_finite) {
+    unsigned lmin = 0xffffffffu, lmax = 0u;
+    unsigned long long cnt = 0;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n_pts; i += (long long)gridDim.x * NT) {
+        const long long pix = idx[i];
+        const long long r = pix / cols, c = pix - r * cols;
+        const long long rr = r + i0 + tba_row0, cc = c + j0;
+        double acc = CUDART_NAN;
+        if (rr >= 0 && rr + 1 < tba_rows_total && cc >= 0 && cc + 1 < cols) {
+            const float* t = tba + rr * tba_ld + cc;
+            acc = w00 * (double)t[0] + w01 * (double)t[1] + w10 * (double)t[tba_ld] + w11 * (double)t[tba_ld + 1];
+        } else if (rr >= 0 && rr < tba_rows_total && cc >= 0 && cc < cols) {
+            const bool row_ok = (rr + 1 < tba_rows_total), col_ok = (cc + 1 < cols);
+            const float* t = tba + rr * tba_ld + cc;
+            acc = w00 * (double)t[0];
+            acc += col_ok ? w01 * (double)t[1] : (w01 != 0.0 ? CUDART_NAN : 0.0);
+            acc += row_ok ? w10 * (double)t[tba_ld] : (w10 != 0.0 ? CUDART_NAN : 0.0);
+            acc += (row_ok && col_ok) ? w11 * (double)t[tba_ld + 1] : (w11 != 0.0 ? CUDART_NAN : 0.0);
+        }
+        const float out = (float)((double)ref[r * ld + c] - acc);
+        dh[i] = out;
+        if (isfinite(out)) {
+            const unsigned a = __float_as_uint(aspect_pts[i]);
+            lmin = min(lmin, a);
+            lmax = max(lmax, a);
+            ++cnt;
+        }
+    }
+    lmin = __reduce_min_sync(0xffffffffu, lmin);
+    lmax = __reduce_max_sync(0xffffffffu, lmax);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) {
+        if (lmin != 0xffffffffu) atomicMin(&asp_minmax[0], lmin);
+        if (lmax != 0u || cnt) atomicMax(&asp_minmax[1], lmax);
+        if (cnt) atomicAdd(n_finite, cnt);
+    }
+}
+
 // Same pass, four pixels per thread (cols % 4 == 0, 16-byte aligned rows): vector loads of ref / mask / aspect, a vector
 // store of dh, and the ten tba values of the four 2x2 stencils loaded up front (memory-level parallelism: the scalar
 // kernel was latency bound, ncu r01b: 29 % of DRAM peak at 31 % issue).  Identical FP64 expressions, identical results.
@@ -485,6 +532,30 @@ int xb_nk_dh(const float* ref_dev, const float* tba_dev, const uint8_t* sub_mask
             ref_dev, tba_dev, sub_mask_dev, aspect_dev, rows, cols, ld, tba_ld, tba_row0, tba_rows_total, (long long)fi,
             (long long)fj, w00, w01, w10, w11, dh_dev, asp_minmax_dev, n_finite_dev);
     }
+    XB_CUDA_CHECK(cudaGetLastError());
+    xb_count_launch(1);
+    return XB_OK;
+}
+
+int xb_nk_dh_points(const float* ref_dev, const float* tba_dev, const int64_t* idx_dev, int64_t n_pts,
+                    const float* aspect_pts_dev, int64_t rows, int64_t cols, int64_t ld, int64_t tba_ld, int64_t tba_row0,
+                    int64_t tba_rows_total, double dx_px, double dy_px, float* dh_dev, uint32_t* asp_minmax_dev,
+                    unsigned long long* n_finite_dev, void* stream) {
+    if (!ref_dev || !tba_dev || !idx_dev || !aspect_pts_dev || !dh_dev || !asp_minmax_dev || !n_finite_dev || n_pts <= 0 ||
+        rows <= 0 || cols <= 0 || ld < cols || tba_ld < cols) {
+        xb_set_error("bad arguments to xb_nk_dh_points");
+        return XB_ERR_INVALID;
+    }
+    if (!isfinite(dx_px) || !isfinite(dy_px) || fabs(dx_px) > 1e9 || fabs(dy_px) > 1e9) {
+        xb_set_error("xb_nk_dh_points: non-finite shift");
+        return XB_ERR_INVALID;
+    }
+    const double fi = floor(dy_px), fj = floor(dx_px);
+    const double fy = dy_px - fi, fx = dx_px - fj;
+    xbn::nk_dh_points_kernel<<<xbn::grid_for(n_pts, 8), xbn::NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        ref_dev, tba_dev, reinterpret_cast<const long long*>(idx_dev), n_pts, aspect_pts_dev, cols, ld, tba_ld, tba_row0,
+        tba_rows_total, (long long)fi, (long long)fj, (1.0 - fy) * (1.0 - fx), (1.0 - fy) * fx, fy * (1.0 - fx), fy * fx,
+        dh_dev, asp_minmax_dev, n_finite_dev);
     XB_CUDA_CHECK(cudaGetLastError());
     xb_count_launch(1);
     return XB_OK;
