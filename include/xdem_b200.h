@@ -336,6 +336,9 @@ int xb_nk_next_keys(const uint32_t* key_dev, const uint8_t* group_dev, int64_t n
  *        moments {n, sum y, sum y^2} at [F_VSHIFT + 5 ..], per-bin medians [F_MED + b]
  * Multi-GPU callers all-gather the sample / compact buffers and all-reduce the counters between the calls (segments:
  * n_seg buffers of seg_cap slots with seg_count filled slots each).  Rasters need cols % 4 == 0 and 16-byte alignment. */
+/* The two full passes (xb_nkf_dh / xb_nkf_y with sample == 0) hand their rows out through queue counters inside
+ * cnt_dev: call xb_nkf_reset before every iteration (xb_nkf_iteration does), otherwise a second full pass finds its
+ * queue exhausted and processes nothing. */
 int xb_nkf_layout(int32_t* out16);
 int xb_nkf_reset(unsigned long long* cnt_dev, uint32_t* keys_dev, double* f64_dev, uint32_t* hist_dev, void* stream);
 /* sample != 0: dh of the jittered row sample (one row of every `stride`) -> sample_dev[(rows+stride-1)/stride * cols]
