@@ -195,7 +195,7 @@ constexpr int FL_TS_PLANE = FL_TS_ROWS * 64;  // floats per plane in a warp's st
 
 // TST: the planes of this row go to the warp's shared-memory staging area (row-major [plane][row][64]; `stg` already
 // points at this row and lane) for a later TMA bulk store instead of to global memory.
-template <unsigned CMASK, bool FAST, bool TST = false>
+template <unsigned CMASK, bool FAST, bool TST = false, int DIR = -1>
 __device__ __forceinline__ void emit_row(const RowFeat2& r0, const RowFeat2& r1, const RowFeat2& r2, const RowFeat2& r3,
                                          const RowFeat2& r4, const TerrainParams& p, long long off, bool full,
                                          int nvalid, float* stg = nullptr) {
@@ -302,8 +302,11 @@ __device__ __forceinline__ void emit_row(const RowFeat2& r0, const RowFeat2& r1,
             const f2 m11 = sub2(r1.E, r3.E), m12 = sub2(r3.D, r1.D), m21 = sub2(r0.E, r4.E), m22 = sub2(r4.D, r0.D);
             const f2 nsxy = fma2(S2(4.0f), m22, fma2(S2(2.0f), add2(m12, m21), m11));
             float r6a[6], r6b[6];
-            curv_alg<float>(sx.x, sy.x, -nsxx.x, -nsyy.x, -nsxy.x, p, CMASK, r6a);
-            curv_alg<float>(sx.y, sy.y, -nsxx.y, -nsyy.y, -nsxy.y, p, CMASK, r6b);
+            // g2 in fp32 exactly as the slope block forms it (and as curv_alg<float> recomputes it)
+            const f2 zxa = mul2(sx, S2(p.f.inv1)), zya = mul2(sy, S2(p.f.inv1));
+            const f2 g2a = fma2(zxa, zxa, mul2(zya, zya));
+            curv_alg_f32<DIR>(sx.x, sy.x, -nsxx.x, -nsyy.x, -nsxy.x, g2a.x, p, CMASK, r6a);
+            curv_alg_f32<DIR>(sx.y, sy.y, -nsxx.y, -nsyy.y, -nsxy.y, g2a.y, p, CMASK, r6b);
 #define XB_FL_PUT_ALG(A)                             \
     if constexpr ((CMASK & (1u << (4 + A))) != 0) \
         put(std::integral_constant<int, 4 + A>{}, r6a[A] + car.x, r6b[A] + car.y);
@@ -313,7 +316,7 @@ __device__ __forceinline__ void emit_row(const RowFeat2& r0, const RowFeat2& r1,
     }
 }
 
-template <bool ALG, unsigned CMASK, bool PACKED>
+template <bool ALG, unsigned CMASK, bool PACKED, int DIR = -1>
 __global__ void __launch_bounds__(NTHREADS, 2)
 florinsky_sliding_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TerrainParams p) {
     constexpr uint32_t STAGE_BYTES = BOXW * FL_BOXH * sizeof(float);
@@ -384,7 +387,7 @@ florinsky_sliding_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
                     const float* rp = base + (size_t)(4 + 5 * g) * BOXW;
 #define XB_FL_STEP(NEW, A, B, C, D, E)                                   \
     make_features(rp, NEW);                                              \
-    if constexpr (PACKED) emit_row<CMASK, true>(A, B, C, D, E, p, off, true, 2);                  \
+    if constexpr (PACKED) emit_row<CMASK, true, false, DIR>(A, B, C, D, E, p, off, true, 2);      \
     else emit_row<ALG, CMASK, true>(A, B, C, D, E, p, off, true, 2);                               \
     rp += BOXW, off += p.out_ld;
                     XB_FL_RING(XB_FL_STEP)
@@ -398,7 +401,7 @@ florinsky_sliding_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 #define XB_FL_STEP(NEW, A, B, C, D, E)                                                            \
     make_features(rp, NEW);                                                                       \
     if (y < p.row_end) {                                                                          \
-        if constexpr (PACKED) emit_row<CMASK, false>(A, B, C, D, E, p, off, full, nvalid);        \
+        if constexpr (PACKED) emit_row<CMASK, false, false, DIR>(A, B, C, D, E, p, off, full, nvalid); \
         else emit_row<ALG, CMASK, false>(A, B, C, D, E, p, off, full, nvalid);                    \
     }                                                                                             \
     rp += BOXW, off += p.out_ld, ++y;
@@ -620,8 +623,16 @@ int launch_florinsky_sliding(const TerrainParams& p_in, cudaStream_t stream) {
 #define XB_FL_CASE(M) \
     case M: return launch_one(florinsky_sliding_kernel<((M) & ~15u) != 0, M, true>);
             XB_FL_CASE(1u) XB_FL_CASE(2u) XB_FL_CASE(3u) XB_FL_CASE(4u) XB_FL_CASE(7u) XB_FL_CASE(8u) XB_FL_CASE(11u)
-            XB_FL_CASE(15u) XB_FL_CASE(0x3F7u) XB_FL_CASE(0x3FFu)
+            XB_FL_CASE(15u)
 #undef XB_FL_CASE
+            // the "all attributes" requests: curvature method fixed at compile time (the other method's arithmetic
+            // drops out of the per-pixel algebra)
+            case 0x3F7u:
+                return p.curv_dir ? launch_one(florinsky_sliding_kernel<true, 0x3F7u, true, 1>)
+                                  : launch_one(florinsky_sliding_kernel<true, 0x3F7u, true, 0>);
+            case 0x3FFu:
+                return p.curv_dir ? launch_one(florinsky_sliding_kernel<true, 0x3FFu, true, 1>)
+                                  : launch_one(florinsky_sliding_kernel<true, 0x3FFu, true, 0>);
             default: break;
         }
     }
