@@ -425,7 +425,7 @@ def extra_c4(ctx: Ctx, args, peak: float, sampler: ClockSampler | None) -> dict:
 def extra_c3(ctx: Ctx, args) -> dict:
     import bench_extra
 
-    a = argparse.Namespace(n=args.c3_n, cpu_n=args.c3_cpu_n, steps=2)
+    a = argparse.Namespace(n=args.c3_n, cpu_n=args.c3_cpu_n, steps=3)
     return bench_extra.bench_variogram(a)  # reuses the process group bench.py initialised
 
 
@@ -695,11 +695,27 @@ def main() -> None:
                 if name == "c1":
                     r = extra_c1(ctx, args, peak) if world == 1 else None
                 elif name == "c3":
+                    t0c = time.perf_counter()
+                    if rank == 0:
+                        sampler.mark_begin()
                     r = extra_c3(ctx, args)
+                    if rank == 0:
+                        sampler.mark_end()
+                        if r:
+                            w = r.pop("timed_window", None) or [t0c, time.perf_counter()]
+                            r["clocks"] = sampler.window(w[0], w[1])
                 elif name == "c4":
                     r = extra_c4(ctx, args, peak, sampler if rank == 0 else None)
                 elif name == "c5":
+                    t0c = time.perf_counter()
+                    if rank == 0:
+                        sampler.mark_begin()
                     r = extra_c5(ctx, args)
+                    if rank == 0:
+                        sampler.mark_end()
+                        if r:
+                            w = r.pop("timed_window", None) or [t0c, time.perf_counter()]
+                            r["clocks"] = sampler.window(w[0], w[1])
                 else:
                     r = {"error": f"unknown extra '{name}'"}
             except Exception as e:  # noqa: BLE001
