@@ -707,15 +707,10 @@ def main() -> None:
                 elif name == "c4":
                     r = extra_c4(ctx, args, peak, sampler if rank == 0 else None)
                 elif name == "c5":
-                    t0c = time.perf_counter()
-                    if rank == 0:
-                        sampler.mark_begin()
+                    # no NVML polling here: the queries take driver locks and this step is 370 small launches + 10 syncs
                     r = extra_c5(ctx, args)
-                    if rank == 0:
-                        sampler.mark_end()
-                        if r:
-                            w = r.pop("timed_window", None) or [t0c, time.perf_counter()]
-                            r["clocks"] = sampler.window(w[0], w[1])
+                    if r:
+                        r.pop("timed_window", None)
                 else:
                     r = {"error": f"unknown extra '{name}'"}
             except Exception as e:  # noqa: BLE001
