@@ -153,6 +153,13 @@ int xb_bin_absdev_keys(const float* values_dev, const uint16_t* bin_dev, int64_t
 int xb_bin_apply_1d(const float* elev_dev, const float* var_dev, int64_t n, const double* x_dev, const double* v_dev,
                     int m, int mode, float* out_dev, void* stream);
 
+/* Per-bin sum / sum of squares (float64) and minimum / maximum (order-preserving uint32 keys of the float32 values) of
+ * the samples xb_bin_keys assigned to bins: the remaining built-in statistics of scipy.stats.binned_statistic ('mean',
+ * 'std', 'sum', 'min', 'max') that nd_binning accepts (spatialstats.py:147-149).  The caller zero-fills sum / sumsq and
+ * sets minkey to 0xffffffff, maxkey to 0. */
+int xb_bin_moments(const float* values_dev, const uint16_t* bin_dev, int64_t n, int n_bins, double* sum_dev,
+                   double* sumsq_dev, uint32_t* minkey_dev, uint32_t* maxkey_dev, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Texture shading (fractional Laplacian, Brown 2010) -- the device stages of `_texture_shading_fft`
  * (xdem/terrain/freq.py:62-148; routed at terrain.py:641-643).  The two FFTs in between are plain library transforms

@@ -72,7 +72,11 @@ def test_host_helpers() -> None:
     assert np.array_equal(xb._key_to_float(np.array([0x80000000 | np.float32(1.5).view(np.uint32)], dtype=np.uint32)),
                           np.array([1.5], dtype=np.float32))
     with pytest.raises(NotImplementedError, match="arbitrary Python callable"):
-        xb._stat_kind(np.nanstd)
+        xb._stat_kind(lambda a: 0.0)
+    with pytest.raises(NotImplementedError, match="not available"):
+        xb._stat_kind("kurtosis")
+    assert xb._stat_kind(np.nanstd) == ("nanstd", "std") and xb._stat_kind("mean") == ("mean", "mean")
+    assert xb._stat_kind(np.nanmax) == ("nanmax", "max") and xb._stat_kind(np.sum) == ("sum", "sum")
     assert xb._stat_kind(np.nanmedian) == ("nanmedian", "median")
     assert xb._stat_kind(xb.nmad) == ("nmad", "nmad")
 
@@ -182,7 +186,39 @@ def test_gpu_statistics_selection_and_edges() -> None:
     _close(df2["nmad"].to_numpy(), ref2["nmad"], "ties nmad")
     assert xs.nmad(v) == pytest.approx(float(bo.nmad(v)), rel=1e-6)
     with pytest.raises(NotImplementedError):
-        xs.nd_binning(v, [x], ["x"], statistics=[np.nanstd])
+        xs.nd_binning(v, [x], ["x"], statistics=[lambda a: float(np.ptp(a))])
+    # the other built-in statistics of scipy.stats.binned_statistic (xb_bin_moments): strings and NumPy callables
+    import scipy.stats
+
+    from xdem_b200 import binning as xbin
+
+    rng = np.random.default_rng(5)
+    vm = (1000 + 30 * rng.standard_normal(200_000)).astype(np.float32)
+    xm = rng.uniform(-1, 1, vm.size).astype(np.float32)
+    ym = rng.uniform(0, 5, vm.size).astype(np.float32)
+    vm[::97] = np.nan
+    stats = ["mean", "std", "sum", "min", "max", np.nanmean, np.nanstd, np.nanmin, np.nanmax, np.nansum]
+    dfm = xs.nd_binning(vm, [xm, ym], ["x", "y"], list_var_bins=(7, 5), statistics=stats)
+    ok = np.isfinite(vm)
+    d1 = dfm[dfm.nd == 1]
+    for var, name, nb in ((xm, "x", 7), (ym, "y", 5)):
+        sub = d1[d1[name].notna()]
+        edges = xbin.bin_edges(float(var[ok].min()), float(var[ok].max()), nb, np.float32)
+        for stat in ("mean", "std", "sum", "min", "max"):
+            ref = scipy.stats.binned_statistic(var[ok], vm[ok].astype(np.float64), statistic=stat, bins=edges)[0]
+            got = sub[stat].to_numpy()
+            assert np.allclose(got, ref, rtol=1e-9 if stat in ("min", "max") else 2e-7, atol=0, equal_nan=True), (name, stat)
+            assert np.array_equal(sub["nan" + stat].to_numpy(), got, equal_nan=True)
+    d2 = dfm[dfm.nd == 2]
+    ex = xbin.bin_edges(float(xm[ok].min()), float(xm[ok].max()), 7, np.float32)
+    ey = xbin.bin_edges(float(ym[ok].min()), float(ym[ok].max()), 5, np.float32)
+    ref2 = scipy.stats.binned_statistic_2d(xm[ok], ym[ok], vm[ok].astype(np.float64), statistic="mean", bins=[ex, ey])[0]
+    assert np.allclose(d2["mean"].to_numpy(), ref2.flatten(), rtol=2e-7, equal_nan=True)
+    # empty bins: NaN for mean / std / min / max, 0 for sum
+    dfe = xs.nd_binning(np.array([1.0, 2.0], dtype=np.float32), [np.array([0.1, 0.2], dtype=np.float32)], ["x"],
+                        list_var_bins=[np.array([0.0, 0.5, 1.0])], statistics=["mean", "sum", "max"])
+    assert dfe["count"].tolist() == [2, 0] and np.isnan(dfe["mean"].iloc[1]) and dfe["sum"].iloc[1] == 0.0
+    assert np.isnan(dfe["max"].iloc[1]) and dfe["max"].iloc[0] == 2.0
 
 
 @pytest.mark.gpu

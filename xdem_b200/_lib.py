@@ -104,6 +104,8 @@ def lib() -> ctypes.CDLL:
                                    c_int64, c_int64, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int64, c_int, c_uint32, c_void_p, c_uint64, c_void_p, c_void_p, c_uint64, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.xb_bin_moments.restype = c_int
+    L.xb_bin_moments.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.xb_nkf_iteration_points.restype = c_int
     L.xb_nkf_iteration_points.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
                                           c_int64, c_int64, c_int64, c_int64, c_double, c_double, c_int, c_void_p,
@@ -165,6 +167,6 @@ EXPORTED = ["xb_last_error", "xb_version", "xb_launch_count", "xb_terrain_fused"
             "xb_windowed_generic", "xb_set_option", "xb_shift_resample", "xb_texture_prepare", "xb_texture_filter",
             "xb_texture_finish", "xb_bin_keys", "xb_bin_hist", "xb_bin_next", "xb_bin_absdev_keys", "xb_probe_stream", "xb_probe_exact_math",
             "xb_terrain_fused_host_rows", "xb_release_scratch", "xb_variogram_pairs_xy",
-            "xb_nkf_layout", "xb_nkf_reset", "xb_nkf_dh", "xb_nkf_range", "xb_nkf_y", "xb_nkf_select", "xb_nkf_finalize", "xb_nkf_iteration", "xb_nk_prepare", "xb_nk_dh_points", "xb_nkf_iteration_points", "xb_bin_apply_1d", "xb_probe_stream_tma"]
+            "xb_nkf_layout", "xb_nkf_reset", "xb_nkf_dh", "xb_nkf_range", "xb_nkf_y", "xb_nkf_select", "xb_nkf_finalize", "xb_nkf_iteration", "xb_nk_prepare", "xb_nk_dh_points", "xb_nkf_iteration_points", "xb_bin_moments", "xb_bin_apply_1d", "xb_probe_stream_tma"]
 
 __all__ = ["lib", "check", "launch_count", "set_option", "XdemB200Error", "LIB_PATH", "EXPORTED"]

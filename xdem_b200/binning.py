@@ -166,8 +166,8 @@ def _select_medians(keys: torch.Tensor, bins: torch.Tensor, n_bins: int) -> tupl
 
 
 def binned_robust_stats(values: torch.Tensor, variables: list[torch.Tensor], edges: list[np.ndarray],
-                        want_median: bool = True, want_nmad: bool = False, nfact: float = NMAD_FACTOR
-                        ) -> dict[str, np.ndarray]:
+                        want_median: bool = True, want_nmad: bool = False, nfact: float = NMAD_FACTOR,
+                        want_moments: bool = False) -> dict[str, np.ndarray]:
     """Counts / medians / NMADs of `values` in the (flattened, C-order) bins spanned by 1-3 `variables` and their edge
     arrays.  All tensors are flat float32 CUDA tensors of one length; samples with a non-finite value or variable, or
     outside the edges, are dropped."""
@@ -184,6 +184,9 @@ def binned_robust_stats(values: torch.Tensor, variables: list[torch.Tensor], edg
         out["count"] = np.zeros(n_bins, dtype=np.int64)
         out["median"] = np.full(n_bins, np.nan, dtype=np.float32)
         out["nmad"] = np.full(n_bins, np.nan, dtype=np.float32)
+        for k in ("mean", "std", "min", "max"):
+            out[k] = np.full(n_bins, np.nan)
+        out["sum"] = np.zeros(n_bins)
         return out
     edges64 = np.concatenate([np.asarray(e, dtype=np.float64) for e in edges])
     edges_t = torch.from_numpy(edges64).to(dev)
@@ -205,25 +208,57 @@ def binned_robust_stats(values: torch.Tensor, variables: list[torch.Tensor], edg
                                             keys.data_ptr(), stream))
             mad, _ = _select_medians(keys, bins, n_bins)
             out["nmad"] = (np.float32(nfact) * mad).astype(np.float32)  # float32 * python float stays float32 (NEP 50)
+        if want_moments:
+            # 'mean' / 'std' / 'sum' / 'min' / 'max' of scipy.stats.binned_statistic: float64 per-bin moments and
+            # order-preserving min / max keys in one pass (xb_bin_moments); empty bins give NaN (0 for 'sum')
+            mom = torch.zeros(2 * n_bins, dtype=torch.float64, device=dev)
+            kmin = torch.full((n_bins,), -1, dtype=torch.int32, device=dev)  # 0xffffffff
+            kmax = torch.zeros(n_bins, dtype=torch.int32, device=dev)
+            _lib.check(L.xb_bin_moments(values.data_ptr(), bins.data_ptr(), n, n_bins, mom.data_ptr(),
+                                        mom.data_ptr() + 8 * n_bins, kmin.data_ptr(), kmax.data_ptr(), stream))
+            mom_h = mom.cpu().numpy()
+            s1, s2 = mom_h[:n_bins], mom_h[n_bins:]
+            c = counts.astype(np.float64)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                mean = np.where(c > 0, s1 / c, np.nan)
+                var = np.where(c > 0, np.maximum(s2 / c - mean * mean, 0.0), np.nan)
+            out["sum"] = s1.copy()
+            out["mean"] = mean
+            out["std"] = np.sqrt(var)  # population standard deviation, as np.std / SciPy's 'std'
+            lo = _key_to_float(kmin.cpu().numpy().view(np.uint32)).astype(np.float64)
+            hi = _key_to_float(kmax.cpu().numpy().view(np.uint32)).astype(np.float64)
+            out["min"] = np.where(c > 0, lo, np.nan)
+            out["max"] = np.where(c > 0, hi, np.nan)
     return out
 
 
+#: statistics computed from the per-bin moments of xb_bin_moments: SciPy's built-in strings and their NumPy callables
+_MOMENT_STATS = {"mean": "mean", "nanmean": "mean", "std": "std", "nanstd": "std", "sum": "sum", "nansum": "sum",
+                 "min": "min", "nanmin": "min", "amin": "min", "max": "max", "nanmax": "max", "amax": "max"}
+
+
 def _stat_kind(stat: Any) -> tuple[str, str]:
-    """(column name as the reference builds it, kernel statistic)."""
+    """(column name as the reference builds it -- the string, or the callable's __name__, spatialstats.py:160-175 --,
+    kernel statistic)."""
     if isinstance(stat, str):
         if stat == "count":
             return "count", "count"
         if stat == "median":
             return "median", "median"
-        raise NotImplementedError(f"statistic '{stat}' is not available in the B200 binning (count, median, nmad)")
+        if stat in ("mean", "std", "sum", "min", "max"):  # scipy.stats.binned_statistic's built-in names
+            return stat, stat
+        raise NotImplementedError(f"statistic '{stat}' is not available in the B200 binning (count, median, mean, std, "
+                                  "sum, min, max, nmad)")
     name = getattr(stat, "__name__", None)
     if stat is np.nanmedian or stat is np.median or name in ("nanmedian", "median"):
         return name or "nanmedian", "median"
     if name == "nmad":
         return "nmad", "nmad"
+    if name in _MOMENT_STATS and getattr(stat, "__module__", "").startswith("numpy"):
+        return name, _MOMENT_STATS[name]
     raise NotImplementedError(
-        f"statistic {name or stat!r} is an arbitrary Python callable; the B200 binning computes count, np.nanmedian and "
-        "nmad on the device (no per-bin Python calls)"
+        f"statistic {name or stat!r} is an arbitrary Python callable; the B200 binning computes count, median, mean, std, "
+        "sum, min, max and nmad on the device (no per-bin Python calls)"
     )
 
 
@@ -253,6 +288,7 @@ def nd_binning(
         statistics.insert(0, "count")  # spatialstats.py:135-137
     kinds = [_stat_kind(s) for s in statistics]
     want_nmad = any(k == "nmad" for _, k in kinds)
+    want_moments = any(k in ("mean", "std", "sum", "min", "max") for _, k in kinds)
 
     vals = _as_f32_device(values).reshape(-1)
     vars_t = [_as_f32_device(v).reshape(-1) for v in list_var]
@@ -281,7 +317,7 @@ def nd_binning(
 
     def frame(idx: tuple[int, ...]) -> Any:
         edges = [all_edges[i] for i in idx]
-        st = binned_robust_stats(vals, [vars_t[i] for i in idx], edges, want_nmad=want_nmad)
+        st = binned_robust_stats(vals, [vars_t[i] for i in idx], edges, want_nmad=want_nmad, want_moments=want_moments)
         df = pd.DataFrame()
         for (name, kind) in kinds:
             col = st[kind]

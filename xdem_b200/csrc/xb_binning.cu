@@ -194,6 +194,46 @@ bin_apply_1d_kernel(const float* __restrict__ elev, const float* __restrict__ va
     }
 }
 
+
+// Per-bin sum, sum of squares, minimum and maximum (the other built-in statistics of scipy.stats.binned_statistic:
+// 'mean', 'std', 'sum', 'min', 'max').  Lanes of a warp that hit the same bin are merged first (__match_any_sync: a few
+// hundred bins and unsorted samples mean several lanes per bin), then one float64 atomic per distinct bin and warp.
+__global__ void __launch_bounds__(NT)
+bin_moments_kernel(const float* __restrict__ val, const unsigned short* __restrict__ bin, long long n, int n_bins,
+                   double* __restrict__ sum, double* __restrict__ sumsq, unsigned* __restrict__ minkey,
+                   unsigned* __restrict__ maxkey) {
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * NT;
+    const long long n_round = (n + stride - 1) / stride * stride;  // uniform trip count: the body holds warp intrinsics
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n_round; i += stride) {
+        unsigned b = NO_BIN;
+        float v = 0.f;
+        if (i < n) b = bin[i], v = val[i];
+        const bool ok = b != NO_BIN && b < (unsigned)n_bins;
+        const unsigned peers = __match_any_sync(0xffffffffu, ok ? b : 0xffffffffu);
+        if (!__any_sync(0xffffffffu, ok)) continue;
+        // every lane reduces over its peer group; the lowest lane of the group publishes
+        double s = 0.0, s2 = 0.0;
+        unsigned kmin = 0xffffffffu, kmax = 0u;
+        const unsigned key = __float_as_uint(v) & 0x80000000u ? ~__float_as_uint(v) : (__float_as_uint(v) | 0x80000000u);
+        unsigned rest = peers;
+        while (rest) {  // peer groups differ between lanes: iterate over the union of set bits
+            const int src = __ffs(rest) - 1;
+            rest &= rest - 1;
+            const float pv = __shfl_sync(peers, v, src);
+            const unsigned pk = __shfl_sync(peers, key, src);
+            s += (double)pv, s2 += (double)pv * (double)pv;
+            kmin = min(kmin, pk), kmax = max(kmax, pk);
+        }
+        if (ok && lane == __ffs(peers) - 1) {
+            atomicAdd(&sum[b], s);
+            atomicAdd(&sumsq[b], s2);
+            atomicMin(&minkey[b], kmin);
+            atomicMax(&maxkey[b], kmax);
+        }
+    }
+}
+
 }  // namespace xbb
 
 extern "C" {
@@ -300,6 +340,20 @@ int xb_bin_apply_1d(const float* elev_dev, const float* var_dev, int64_t n, cons
     const int grid = (int)(need < (long long)sms * 8 ? need : (long long)sms * 8);
     xbb::bin_apply_1d_kernel<<<grid, 256, (size_t)(2 * m + 1) * sizeof(double), reinterpret_cast<cudaStream_t>(stream)>>>(
         elev_dev, var_dev, n, x_dev, v_dev, m, mode, out_dev);
+    XB_CUDA_CHECK(cudaGetLastError());
+    xb_count_launch(1);
+    return XB_OK;
+}
+
+int xb_bin_moments(const float* values_dev, const uint16_t* bin_dev, int64_t n, int n_bins, double* sum_dev,
+                   double* sumsq_dev, uint32_t* minkey_dev, uint32_t* maxkey_dev, void* stream) {
+    if (!values_dev || !bin_dev || !sum_dev || !sumsq_dev || !minkey_dev || !maxkey_dev || n <= 0 || n_bins < 1 ||
+        n_bins >= 0xFFFF) {
+        xb_set_error("bad arguments to xb_bin_moments");
+        return XB_ERR_INVALID;
+    }
+    xbb::bin_moments_kernel<<<xbb::grid_1d(n, xbb::NT, 8), xbb::NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        values_dev, bin_dev, n, n_bins, sum_dev, sumsq_dev, minkey_dev, maxkey_dev);
     XB_CUDA_CHECK(cudaGetLastError());
     xb_count_launch(1);
     return XB_OK;
