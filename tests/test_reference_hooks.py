@@ -44,7 +44,8 @@ def test_install_routes_reference_terrain_calls_through_the_streamed_seam(ref, m
         out = ref.terrain.get_terrain_attribute(dem, ["hillshade", "roughness", "slope", "rugosity"], resolution=5.0,
                                                 hillshade_azimuth=200.0, hillshade_z_factor=2.0, window_size=5)
     finally:
-        ref.terrain._get_surface_attributes, ref.terrain._get_windowed_indexes = saved
+        xdem_b200.uninstall()
+    assert (ref.terrain._get_surface_attributes, ref.terrain._get_windowed_indexes) == saved
     assert len(out) == 4 and all(o.shape == (6, 8) and o.dtype == np.float32 for o in out)
     surf = [c for c in calls if c["surf"]]
     win = [c for c in calls if c["win"]]
@@ -94,8 +95,9 @@ def test_install_rebinds_nuth_kaab_and_variogram_pair_functions(ref, monkeypatch
                                                                 "bin_statistic": np.nanmean}, **common) == "reference"
         assert hook2(ref_elev=object(), tba_elev=a, params_fit_or_bin={}, **common) == "reference"
     finally:
-        (ref.terrain._get_surface_attributes, ref.terrain._get_windowed_indexes, ref.coreg_affine.nuth_kaab,
-         ref.spatialstats._get_pdist_empirical_variogram, ref.spatialstats._get_cdist_empirical_variogram) = saved
+        xdem_b200.uninstall()
+    assert (ref.terrain._get_surface_attributes, ref.terrain._get_windowed_indexes, ref.coreg_affine.nuth_kaab,
+            ref.spatialstats._get_pdist_empirical_variogram, ref.spatialstats._get_cdist_empirical_variogram) == saved
 
 
 def test_equidistant_parameter_split_equals_reference(ref) -> None:
@@ -107,3 +109,24 @@ def test_equidistant_parameter_split_equals_reference(ref) -> None:
         want = ref.spatialstats._choose_cdist_equidistant_sampling_parameters(extent=ext, shape=shape, subsample=sub)
         got = xs._choose_cdist_equidistant_sampling_parameters(extent=ext, shape=shape, subsample=sub)
         assert got == want
+
+
+def test_uninstall_restores_the_reference_functions(ref) -> None:
+    """install() twice then uninstall(): every rebound name is the reference's own object again (install is idempotent:
+    the nuth_kaab hook always wraps the ORIGINAL function, never an earlier hook)."""
+    import xdem_b200
+
+    names = [(ref.terrain, "_get_surface_attributes"), (ref.terrain, "_get_windowed_indexes"),
+             (ref.coreg_affine, "nuth_kaab"), (ref.spatialstats, "_get_pdist_empirical_variogram"),
+             (ref.spatialstats, "_get_cdist_empirical_variogram")]
+    originals = [getattr(m, n) for m, n in names]
+    try:
+        xdem_b200.install()
+        first_hook = ref.coreg_affine.nuth_kaab
+        xdem_b200.install()
+        assert ref.coreg_affine.nuth_kaab.__wrapped__ is originals[2] and first_hook.__wrapped__ is originals[2]
+        assert all(getattr(m, n) is not o for (m, n), o in zip(names, originals))
+    finally:
+        xdem_b200.uninstall()
+    assert all(getattr(m, n) is o for (m, n), o in zip(names, originals))
+    xdem_b200.uninstall()  # a second call is a no-op
