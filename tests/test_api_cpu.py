@@ -126,6 +126,8 @@ def test_install_rebinds_reference_seam(monkeypatch) -> None:
     xdem_b200.install()
     assert fake_mod._get_surface_attributes is _get_surface_attributes
     assert fake_mod._get_windowed_indexes is _get_windowed_indexes
+    xdem_b200.uninstall()
+    assert fake_mod._get_surface_attributes() == "cpu" and fake_mod._get_windowed_indexes() == "cpu"
 
 
 def test_variogram_and_coreg_validation_without_gpu() -> None:

@@ -20,12 +20,11 @@ from .terrain import get_terrain_attribute  # noqa: F401
 
 __version__ = "0.1.0"
 
-_ORIGINALS: dict[tuple[str, str], object] = {}  # (module, name) -> what install() replaced
+_ORIGINALS: dict[tuple[int, str], tuple[object, object]] = {}  # (id(module), name) -> (module, what install() replaced)
 
 
 def _rebind(module: object, name: str, new: object) -> None:
-    key = (getattr(module, "__name__", str(module)), name)
-    _ORIGINALS.setdefault(key, getattr(module, name))
+    _ORIGINALS.setdefault((id(module), name), (module, getattr(module, name)))
     setattr(module, name, new)
 
 
@@ -61,7 +60,7 @@ def install() -> None:
     if ref_affine is not None and hasattr(ref_affine, "nuth_kaab"):
         from . import coreg
 
-        original = _ORIGINALS.get((ref_affine.__name__, "nuth_kaab"), ref_affine.nuth_kaab)  # idempotent install()
+        original = _ORIGINALS.get((id(ref_affine), "nuth_kaab"), (None, ref_affine.nuth_kaab))[1]  # idempotent install()
         _rebind(ref_affine, "nuth_kaab", coreg.make_reference_hook(original))
 
     try:
@@ -78,8 +77,6 @@ def install() -> None:
 
 def uninstall() -> None:
     """Undo ``install()``: put the reference's own functions back."""
-    import importlib
-
-    for (mod_name, name), original in list(_ORIGINALS.items()):
-        setattr(importlib.import_module(mod_name), name, original)
+    for (_, name), (module, original) in list(_ORIGINALS.items()):
+        setattr(module, name, original)
     _ORIGINALS.clear()
